@@ -1,0 +1,295 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the CPU oracle and the
+reference's golden vectors.  Bit-exact is the bar: byte-identical frame streams, identical PCM."""
+import ctypes as C
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import torch
+    assert torch.cuda.is_available()
+    m = importlib.import_module("x3-rust_b200")
+    m._lib.lib()
+    return m
+
+
+@pytest.fixture(scope="module")
+def dev(pkg):
+    return importlib.import_module("x3-rust_b200.device")
+
+
+def mk_params(pkg, oracle, block_len=20, bpf=500, codes=(0, 1, 3), th=(3, 8, 20)):
+    return pkg.x3.Parameters(block_len, bpf, codes, th), oracle.Params.make(block_len, bpf, codes, th)
+
+
+def signals(oracle):
+    rng = np.random.default_rng(7)
+    return {
+        "s1": oracle.synth(1, 0x58330001, 44100, 0, 64000),
+        "s2": oracle.synth(2, 0x58330002, 384000, 384000 * 2 - 40000, 90000),
+        "s2click": oracle.synth(2, 0x58330002, 384000, 196608 - 500, 21000),
+        "s4": oracle.synth(4, 0x58330004, 384000, 0, 120000),
+        "zeros": np.zeros(30000, dtype=np.int16),
+        "white": rng.integers(-32768, 32768, 45678, dtype=np.int16),
+        "clip": np.where(rng.integers(0, 2, 20001) > 0, 32767, -32768).astype(np.int16),
+        "small": rng.integers(-3, 4, 50001, dtype=np.int16),
+    }
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference's own vectors through the GPU path
+# ---------------------------------------------------------------------------------------------------
+def test_golden_encode_frame(pkg, golden):
+    p = pkg.x3.Parameters.default()
+    for name in ("test_encode_frame", "test_encode_frame_zeros"):       # encoder.rs:342-491
+        g = golden[name]
+        buf = bytearray(0x0eff * 2)
+        w = pkg.bytewriter.SliceByteWriter(buf)
+        stats = [0] * 6
+        pkg.encoder.encode_frame(np.array(g["wav"], dtype=np.int16), w, p, stats)
+        assert list(buf[:w.stream_position()]) == g["expected"], name
+        assert sum(stats) == len(g["wav"]) - 1
+
+
+def test_golden_encode_blocks(pkg, golden):
+    """encoder.rs:494-620: block vectors, embedded as the only block of a 21-sample frame."""
+    p = pkg.x3.Parameters.default()
+    for name in ("test_x3_encode_block", "test_x3_encode_block_bpf_eq16", "test_x3_encode_block_bpf_lt16"):
+        g = golden[name]
+        data, _ = pkg.encoder.encode_array(np.array(g["wav"], dtype=np.int16), p)
+        payload = bytes(data[20:])
+        # payload = 16 bits first sample + block bits; the vector = block bits then word_align
+        bits = "".join("{:08b}".format(b) for b in payload)[16:]
+        exp = "".join("{:08b}".format(b) for b in g["expected"])
+        n = min(len(bits), len(exp))
+        assert bits[:n] == exp[:n] and set(bits[n:] + exp[n:]) <= {"0"}, name
+
+
+def test_golden_decode_blocks(pkg, golden):
+    """decoder.rs:257-355: block vectors wrapped as <first sample><block bits> payloads."""
+    p = pkg.x3.Parameters.default()
+    for name in ("test_decode_block_ftype_1", "test_decode_block_ftype_2", "test_decode_block_ftype_3",
+                 "test_decode_block_bpf_eq16", "test_decode_block_bpf_lt16"):
+        g = golden[name]
+        inp = bytes(g["x3_inp"])
+        if g["first_sample_prefix"]:
+            payload = inp
+        else:  # explicit last_wav and a 6-bit skip: rebuild the stream bit-wise
+            bits = "".join("{:08b}".format(b) for b in inp)[g["skip_bits"]:]
+            bits = "{:016b}".format(g["last_wav"] & 0xffff) + bits
+            bits += "0" * (-len(bits) % 16)
+            payload = int(bits, 2).to_bytes(len(bits) // 8, "big")
+        k = len(g["expected"])
+        out = np.zeros(k + 1, dtype=np.int16)
+        n = pkg.decoder.decode_frame(payload, out, p, k + 1)
+        assert n == k + 1 and list(out[1:]) == g["expected"], name
+
+
+# ---------------------------------------------------------------------------------------------------
+# encode / decode parity against the oracle
+# ---------------------------------------------------------------------------------------------------
+def test_encode_matches_oracle_default(pkg, oracle):
+    p = pkg.x3.Parameters.default()
+    for name, pcm in signals(oracle).items():
+        for n in sorted({pcm.size, 1, 2, 19, 20, 21, 22, 9999, 10000, 10001, 10021, 20000, 29999}):
+            if n > pcm.size:
+                continue
+            ref, rstats = oracle.encode(pcm[:n])
+            got, stats = pkg.encoder.encode_array(pcm[:n], p)
+            assert got.size == ref.size and np.array_equal(got, ref), (name, n)
+            assert stats == rstats, (name, n)
+
+
+def test_encode_matches_oracle_other_params(pkg, oracle):
+    sig = signals(oracle)
+    cases = [dict(bpf=10), dict(bpf=1), dict(block_len=1, bpf=7), dict(block_len=7, bpf=33),
+             dict(block_len=60, bpf=100), dict(block_len=33, bpf=700), dict(codes=(0, 1, 2)),
+             dict(codes=(1, 2, 3), th=(5, 11, 20)), dict(codes=(0, 0, 0), th=(1, 2, 6)),
+             dict(block_len=16, bpf=64, codes=(3, 1, 0), th=(3, 8, 6)), dict(th=(8, 3, 20)), dict(th=(3, 8, 2)),
+             dict(bpf=1200), dict(block_len=5, bpf=3000)]
+    for kw in cases:
+        p, po = mk_params(pkg, oracle, **kw)
+        for name in ("s1", "s2", "s4", "white", "small"):
+            pcm = sig[name][:30000]
+            try:
+                ref, rstats = oracle.encode(pcm, po)
+            except oracle.OracleError as e:
+                assert e.code == -100
+                continue
+            got, stats = pkg.encoder.encode_array(pcm, p)
+            assert got.size == ref.size and np.array_equal(got, ref), (kw, name)
+            assert stats == rstats
+
+
+def test_decode_matches_input(pkg, oracle):
+    p = pkg.x3.Parameters.default()
+    for name, pcm in signals(oracle).items():
+        for n in (pcm.size, 20000, 10000, 10001, 1, 2, 21):
+            n = min(n, pcm.size)
+            stream, _ = oracle.encode(pcm[:n])
+            out, res = pkg.decoder.decode_stream(stream, p)
+            assert res.code == 0 and res.frame_errors == 0 and not res.used_host_walk, (name, n)
+            assert out.size == n and np.array_equal(out, pcm[:n]), (name, n)
+
+
+def test_decode_other_params(pkg, oracle):
+    sig = signals(oracle)
+    for kw in (dict(bpf=10), dict(block_len=7, bpf=33), dict(block_len=60, bpf=100), dict(bpf=4), dict(bpf=8)):
+        p, po = mk_params(pkg, oracle, **kw)
+        for name in ("s1", "s4", "white"):
+            pcm = sig[name][:12000]
+            stream, _ = oracle.encode(pcm, po)
+            out, res = pkg.decoder.decode_stream(stream, p)
+            assert res.code == 0 and np.array_equal(out, pcm), (kw, name)
+
+
+def test_round_trip_c1(pkg, oracle):
+    """BASELINE config 1: 60 s of S1 at 44.1 kHz, 265 frames (last has 6000 samples), whole stream byte-exact."""
+    p = pkg.x3.Parameters.default()
+    pcm = oracle.synth(1, 0x58330001, 44100, 0, 2646000)
+    ref, rstats = oracle.encode(pcm)
+    got, stats = pkg.encoder.encode_array(pcm, p)
+    assert np.array_equal(got, ref) and stats == rstats
+    out, res = pkg.decoder.decode_stream(got, p)
+    assert res.code == 0 and res.frames == 265 and np.array_equal(out, pcm)
+
+
+# ---------------------------------------------------------------------------------------------------
+# corrupt streams: same verdict and same surviving samples as the reference's loop
+# ---------------------------------------------------------------------------------------------------
+def test_corrupt_streams_match_oracle(pkg, oracle):
+    p = pkg.x3.Parameters.default()
+    rng = np.random.default_rng(11)
+    pcm = oracle.synth(2, 0x58330002, 384000, 0, 55000)
+    stream, _ = oracle.encode(pcm)
+    cases = []
+    for _ in range(12):   # payload bit flips -> payload CRC error at that frame
+        s = stream.copy(); s[int(rng.integers(40, s.size))] ^= 1 << int(rng.integers(0, 8)); cases.append(s)
+    for off in (0, 1, 2, 3, 4, 5, 6, 7, 16, 17, 18, 19):   # header damage in frame 0 and in a later frame
+        s = stream.copy(); s[off] ^= 0x10; cases.append(s)
+        h = oracle.read_frame_header(bytes(stream[:20]))
+        s = stream.copy(); s[20 + h.payload_len + off] ^= 0x04; cases.append(s)
+    for cut in (1, 2, 7, 8, 19, 20, 21, 22, 100, 2000):     # truncation
+        cases.append(stream[:stream.size - cut].copy())
+    cases.append(np.concatenate([stream, np.zeros(8, dtype=np.uint8)]))    # short tail: ignored
+    cases.append(np.concatenate([stream, np.zeros(64, dtype=np.uint8)]))   # long tail: header error
+    cases.append(np.concatenate([stream, stream[:300]]))                   # valid header, truncated payload
+    for i, s in enumerate(cases):
+        rc, ref, frames_ok, ferr = oracle.decode_stream(s, pcm.size + 20000)
+        out, res = pkg.decoder.decode_stream(s, p, max_samples=pcm.size + 20000)
+        assert res.code == rc, (i, res.code, rc)
+        assert res.frames == frames_ok and res.frame_errors == ferr, i
+        assert out.size == ref.size and np.array_equal(out, ref), i
+
+
+def test_crafted_payloads_with_valid_crc(pkg, oracle):
+    """Frames whose CRCs are right but whose payload is malformed (bit flips re-sealed with a fresh CRC):
+    the GPU path must stop where the reference stops and agree on every sample it keeps."""
+    p = pkg.x3.Parameters.default()
+    rng = np.random.default_rng(5)
+    pcm = oracle.synth(4, 0x58330004, 384000, 0, 30000)
+    stream, _ = oracle.encode(pcm)
+    h0 = oracle.read_frame_header(bytes(stream[:20]))
+    for trial in range(40):
+        s = stream.copy()
+        pos = 20 + h0.payload_len            # damage frame 1
+        h = oracle.read_frame_header(bytes(s[pos:pos + 20]))
+        pl = s[pos + 20:pos + 20 + h.payload_len]
+        if trial % 4 == 0:
+            pl[int(rng.integers(h.payload_len // 2, h.payload_len)):] = 0      # zero tail
+        else:
+            for _ in range(int(rng.integers(1, 4))):
+                pl[int(rng.integers(0, h.payload_len))] ^= 1 << int(rng.integers(0, 8))
+        s[pos:pos + 20] = np.frombuffer(oracle.write_frame_header(h.samples, 1, h.payload_len, oracle.crc16(pl)), dtype=np.uint8)
+        rc, ref, frames_ok, ferr = oracle.decode_stream(s, pcm.size)
+        out, res = pkg.decoder.decode_stream(s, p, max_samples=pcm.size)
+        assert (res.code, res.frames, res.frame_errors) == (rc, frames_ok, ferr), trial
+        assert np.array_equal(out, ref), trial
+
+
+# ---------------------------------------------------------------------------------------------------
+# device-resident API, generators, file wrappers
+# ---------------------------------------------------------------------------------------------------
+def test_device_generators_match_oracle(dev, oracle):
+    for kind, seed, fs, n0 in ((1, 0x58330001, 44100, 0), (2, 0x58330002, 384000, 384000 - 5000),
+                               (2, 0x58330005, 96000, 96000 * 3 - 100), (4, 0x58330004, 384000, 4096 * 7 - 33),
+                               (2, 0x58330002, 384000, 196608 * 5 - 10)):
+        ref = oracle.synth(kind, seed, fs, n0, 30000)
+        got = dev.synth(kind, seed, fs, n0, 30000).cpu().numpy()
+        assert np.array_equal(got, ref), (kind, seed, fs, n0)
+
+
+def test_device_resident_round_trip(pkg, dev, oracle):
+    import torch
+    p = pkg.x3.Parameters.default()
+    n = 64 * 10000 + 1234
+    pcm = dev.synth(2, 0x58330002, 384000, 384000 - 300000, n)
+    before = dev.kernel_launch_count()
+    out, length, stats = dev.encode_tensor(pcm, p)
+    assert dev.kernel_launch_count() == before + 1
+    ref, rstats = oracle.encode(pcm.cpu().numpy())
+    assert length == ref.size and np.array_equal(out[:length].cpu().numpy(), ref) and stats == rstats
+    dec, ns, res, code = dev.decode_tensor(out, length, p, max_samples=n)
+    assert code == 0 and ns == n and res.frames == 65 and not res.used_host_walk
+    assert torch.equal(dec[:n], pcm)
+    # capacity errors are reported, not crashes
+    small = torch.empty(length - 2, dtype=torch.uint8, device="cuda")
+    with pytest.raises(pkg.X3Error) as e:
+        dev.encode_tensor(pcm, p, out=small)
+    assert e.value.code == pkg.error.BYTEWRITER_INSUFFICIENT_MEMORY
+    # unaligned stream start -> host walk fallback, same answer
+    shifted = torch.empty(length + 2, dtype=torch.uint8, device="cuda")
+    shifted[2:] = out[:length]
+    dec2, ns2, res2, code2 = dev.decode_tensor(shifted[2:], length, p, max_samples=n)
+    assert code2 == 0 and ns2 == n and res2.used_host_walk and torch.equal(dec2[:n], pcm)
+
+
+def test_file_wrappers_round_trip(pkg, oracle, tmp_path):
+    import wave
+    pcm = oracle.synth(1, 0x58330001, 44100, 0, 123456)
+    wav_in, x3a, wav_out = tmp_path / "in.wav", tmp_path / "a.x3a", tmp_path / "out.wav"
+    with wave.open(str(wav_in), "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(44100); w.writeframes(pcm.tobytes())
+    pkg.wav_to_x3a(wav_in, x3a, quiet=True)
+    ref, _ = oracle.x3a_encode(pcm, 44100)
+    assert x3a.read_bytes() == ref.tobytes()
+    pkg.x3a_to_wav(x3a, wav_out, quiet=True)
+    with wave.open(str(wav_out), "rb") as w:
+        assert (w.getnchannels(), w.getsampwidth(), w.getframerate()) == (1, 2, 44100)
+        got = np.frombuffer(w.readframes(w.getnframes()), dtype=np.int16)
+    assert np.array_equal(got, pcm)
+    assert os.path.getsize(wav_out) == 44 + 2 * pcm.size
+    rc, opcm, fs, frames_ok, ferr = oracle.x3a_decode(ref, pcm.size)
+    assert rc == 0 and fs == 44100 and np.array_equal(opcm, pcm)
+
+
+def test_library_api_forms(pkg, oracle):
+    """The README form (x3.Channel + slice writer) and the current form (IterChannel + ByteWriter)."""
+    x3m = pkg.x3
+    pcm = oracle.synth(1, 0x58330001, 44100, 0, 25000)
+    ref, _ = oracle.encode(pcm)
+    buf = bytearray(pcm.size * 2 + 1)
+    w = pkg.bytewriter.SliceByteWriter(buf)
+    w.write_all(b"\x55")                                    # odd start: encode_frame aligns to 2 (encoder.rs:182)
+    pkg.encoder.encode([x3m.Channel(0, pcm, 44100, x3m.Parameters.default())], w, quiet=True)
+    assert bytes(buf[2:w.stream_position()]) == ref.tobytes() and buf[1] == 0
+    buf2 = bytearray(ref.size)
+    w2 = pkg.bytewriter.SliceByteWriter(buf2)
+    pkg.encoder.encode([x3m.IterChannel(0, iter(pcm.tolist()), 44100, x3m.Parameters.default())], w2, quiet=True)
+    assert bytes(buf2) == ref.tobytes()
+    with pytest.raises(pkg.X3Error) as e:
+        pkg.encoder.encode([x3m.Channel(0, pcm, 44100, x3m.Parameters.default())],
+                           pkg.bytewriter.SliceByteWriter(bytearray(ref.size - 1)), quiet=True)
+    assert e.value.code == pkg.error.BYTEWRITER_INSUFFICIENT_MEMORY
+    ch = x3m.Channel(0, pcm, 44100, x3m.Parameters.default())
+    with pytest.raises(pkg.X3Error) as e:
+        pkg.encoder.encode([ch, ch], pkg.bytewriter.SliceByteWriter(bytearray(10)), quiet=True)
+    assert e.value.code == pkg.error.MORE_THAN_ONE_CHANNEL

@@ -1,0 +1,640 @@
+// x3_api.cu -- the C ABI of include/x3_b200.h over the CUDA kernels.  No CPU fallback: every computing
+// entry point fails with X3_ERR_CUDA when no device is usable.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/x3_b200.h"
+#include "x3_crc_host.h"
+#include "x3_dec_core.cuh"
+#include "x3_enc_core.cuh"
+#include "x3_kernels.h"
+
+using namespace x3;
+
+namespace {
+
+std::atomic<uint64_t> g_launches{0};
+thread_local char tl_cuda_err[256] = "";
+thread_local float tl_ms[4] = {0.f, 0.f, 0.f, 0.f};
+
+int cuda_fail(cudaError_t e, const char *what) {
+  snprintf(tl_cuda_err, sizeof tl_cuda_err, "%s: %s", what, cudaGetErrorString(e));
+  cudaGetLastError();
+  return X3_ERR_CUDA;
+}
+#define CU(call)                                         \
+  do {                                                   \
+    cudaError_t e__ = (call);                            \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+// ---- CRC table bank (layout in x3_common.cuh) -------------------------------------------------
+uint16_t g_crc_host[kCrcTableEntries];
+std::once_flag g_crc_once;
+
+void build_crc_host() { build_crc_bank(g_crc_host); }
+const uint16_t *crc_host() {
+  std::call_once(g_crc_once, build_crc_host);
+  return g_crc_host;
+}
+
+struct DeviceState {
+  uint16_t *crc_dev = nullptr;
+  int sms = 0;
+  bool pool_ready = false;
+};
+std::mutex g_dev_mu;
+DeviceState g_dev[64];
+
+int device_state(DeviceState **out) {
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return X3_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  DeviceState &d = g_dev[dev];
+  if (!d.crc_dev) {
+    CU(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+    uint16_t *p = nullptr;
+    CU(cudaMalloc(&p, sizeof(uint16_t) * kCrcTableEntries));
+    CU(cudaMemcpy(p, crc_host(), sizeof(uint16_t) * kCrcTableEntries, cudaMemcpyHostToDevice));
+    d.crc_dev = p;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t thr = UINT64_MAX;  // keep freed workspace cached in the pool between calls
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+      d.pool_ready = true;
+    }
+    cudaGetLastError();
+  }
+  *out = &d;
+  return X3_OK;
+}
+
+// small pinned buffer for result read-back, one per thread
+struct Pinned {
+  unsigned long long *p = nullptr;
+  ~Pinned() { if (p) cudaFreeHost(p); }
+};
+thread_local Pinned tl_pinned;
+int pinned(unsigned long long **out) {
+  if (!tl_pinned.p) CU(cudaMallocHost(&tl_pinned.p, 64 * sizeof(unsigned long long)));
+  *out = tl_pinned.p;
+  return X3_OK;
+}
+
+struct Timer {
+  cudaEvent_t a = nullptr, b = nullptr;
+  cudaStream_t s;
+  explicit Timer(cudaStream_t st) : s(st) {
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+  }
+  ~Timer() {
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+  }
+  void start() { cudaEventRecord(a, s); }
+  void stop() { cudaEventRecord(b, s); }
+  float ms() {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, a, b) != cudaSuccess) { cudaGetLastError(); return 0.f; }
+    return t;
+  }
+};
+
+// ---- parameter handling -----------------------------------------------------------------------
+constexpr size_t kMaxDynSmem = 227 * 1024;
+
+struct Derived {
+  CodecParams P;
+  uint32_t max_blocks;
+  uint32_t max_block_bits;
+  uint32_t out_words_cap;
+  bool fast;
+  size_t smem;
+};
+
+uint32_t max_block_bits_of(const x3_params *p) {
+  const bool sorted = p->thresholds[0] <= p->thresholds[1] && p->thresholds[1] <= p->thresholds[2];
+  uint32_t rice_max = 0;
+  for (int f = 0; f < 3; f++) {
+    uint32_t t = sorted ? p->thresholds[f] : p->thresholds[2];
+    if (t > p->thresholds[2]) t = p->thresholds[2];
+    uint32_t l = ((2u * t) >> p->codes[f]) + p->codes[f] + 1u;
+    if (l > rice_max) rice_max = l;
+  }
+  uint32_t a = 2u + p->block_len * rice_max, b = 6u + 16u * p->block_len;
+  return a > b ? a : b;
+}
+
+int derive(const x3_params *p, Derived *d) {
+  if (!p) return X3_ERR_INVALID_ARGUMENT;
+  if (p->block_len == 0 || p->blocks_per_frame == 0) return X3_ERR_INVALID_ARGUMENT;
+  for (int k = 0; k < 3; k++)
+    if (p->codes[k] > 3) return X3_ERR_INVALID_ARGUMENT;  // RiceCodes::get would index out of bounds, x3.rs:256
+  for (int k = 0; k < 2; k++)                              // x3.rs:107-112
+    if (p->thresholds[k] > rice_offset(p->codes[k])) return X3_ERR_INVALID_ENCODING_THRESH;
+  if (p->block_len > (uint32_t)kMaxBlockLen) return X3_ERR_UNSUPPORTED_PARAMS;  // reference panics (wav_diff[60])
+  if (p->thresholds[2] > 4096u) return X3_ERR_UNSUPPORTED_PARAMS;
+  const unsigned long long spf = (unsigned long long)p->block_len * p->blocks_per_frame;
+  if (spf > 65535ull) return X3_ERR_UNSUPPORTED_PARAMS;  // header field is u16 (encoder.rs:141)
+  d->P.block_len = p->block_len;
+  d->P.spf = (uint32_t)spf;
+  for (int k = 0; k < 3; k++) { d->P.codes[k] = p->codes[k]; d->P.thresholds[k] = p->thresholds[k]; }
+  d->max_blocks = p->blocks_per_frame;
+  d->max_block_bits = max_block_bits_of(p);
+  const unsigned long long bits = 16ull + (unsigned long long)d->max_blocks * d->max_block_bits;
+  d->out_words_cap = (uint32_t)((bits + 31ull) / 32ull) + 1u;
+  d->fast = params_are_default(d->P);
+  d->smem = encode_smem_bytes(d->P, d->max_blocks, d->out_words_cap);
+  if (d->smem > kMaxDynSmem) return X3_ERR_UNSUPPORTED_PARAMS;
+  return X3_OK;
+}
+
+size_t frame_bound(uint32_t n, const Derived &d) {
+  const uint32_t nblk = n > 1 ? (n - 2u) / d.P.block_len + 1u : 1u;
+  const unsigned long long bits = 16ull + (unsigned long long)nblk * d.max_block_bits;
+  return (size_t)kFrameHeaderLen + (size_t)(((bits + 15ull) >> 4) << 1);
+}
+
+int map_frame_error(int st) { return st; }  // kDec* codes are the public X3_ERR_* values
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int x3_abi_version(void) { return X3_B200_ABI_VERSION; }
+
+int x3_params_default(x3_params *p) {
+  if (!p) return X3_ERR_INVALID_ARGUMENT;
+  p->block_len = 20;
+  p->blocks_per_frame = 500;
+  p->codes[0] = 0; p->codes[1] = 1; p->codes[2] = 3;
+  p->thresholds[0] = 3; p->thresholds[1] = 8; p->thresholds[2] = 20;
+  return X3_OK;
+}
+
+int x3_params_validate(const x3_params *p) {
+  Derived d;
+  return derive(p, &d);
+}
+
+size_t x3_encode_bound(size_t n_samples, const x3_params *p) {
+  Derived d;
+  if (derive(p, &d) != X3_OK || n_samples == 0) return 0;
+  const size_t full = n_samples / d.P.spf, rem = n_samples % d.P.spf;
+  size_t b = full * frame_bound(d.P.spf, d);
+  if (rem) b += frame_bound((uint32_t)rem, d);
+  return b;
+}
+
+const char *x3_strerror(int code) {
+  switch (code) {
+    case X3_OK: return "ok";
+    case X3_ERR_INVALID_ENCODING_THRESH: return "InvalidEncodingThresh: threshold must be <= code.offset";
+    case X3_ERR_OUT_OF_BOUNDS_INVERSE: return "OutOfBoundsInverse";
+    case X3_ERR_MORE_THAN_ONE_CHANNEL: return "MoreThanOneChannel";
+    case X3_ERR_ARCHIVE_XML_INVALID: return "ArchiveHeaderXMLInvalid";
+    case X3_ERR_ARCHIVE_XML_RICE_CODE: return "ArchiveHeaderXMLRiceCode";
+    case X3_ERR_ARCHIVE_INVALID_KEY: return "ArchiveHeaderXMLInvalidKey";
+    case X3_ERR_FRAME_LENGTH: return "FrameLength";
+    case X3_ERR_FRAME_HEADER_INVALID_KEY: return "FrameHeaderInvalidKey";
+    case X3_ERR_FRAME_HEADER_INVALID_PAYLOAD_LEN: return "FrameHeaderInvalidPayloadLen";
+    case X3_ERR_FRAME_HEADER_INVALID_HEADER_CRC: return "FrameHeaderInvalidHeaderCRC";
+    case X3_ERR_FRAME_HEADER_INVALID_PAYLOAD_CRC: return "FrameHeaderInvalidPayloadCRC";
+    case X3_ERR_FRAME_DECODE_INVALID_FTYPE: return "FrameDecodeInvalidFType";
+    case X3_ERR_FRAME_DECODE_INVALID_BPF: return "FrameDecodeInvalidBPF";
+    case X3_ERR_FRAME_DECODE_UNEXPECTED_END: return "FrameDecodeUnexpectedEnd";
+    case X3_ERR_BYTEWRITER_INSUFFICIENT_MEMORY: return "ByteWriterInsufficientMemory";
+    case X3_ERR_IO: return "Io: unexpected end of stream";
+    case X3_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case X3_ERR_UNSUPPORTED_PARAMS: return "parameters outside the GPU path's limits";
+    case X3_ERR_CUDA: return "CUDA error (see x3_last_cuda_error)";
+    case X3_ERR_REFERENCE_PANIC: return "input on which the reference panics";
+    default: return "unknown error";
+  }
+}
+
+const char *x3_last_cuda_error(void) { return tl_cuda_err; }
+uint64_t x3_kernel_launch_count(void) { return g_launches.load(); }
+int x3_last_kernel_ms(float ms[4]) {
+  if (!ms) return X3_ERR_INVALID_ARGUMENT;
+  ms[0] = tl_ms[0]; ms[1] = tl_ms[1]; ms[2] = tl_ms[2]; ms[3] = tl_ms[3];
+  return X3_OK;
+}
+
+uint16_t x3_crc16(const uint8_t *data, size_t len) {
+  const uint16_t *T = crc_host();
+  uint32_t s = 0xffffu;
+  for (size_t i = 0; i < len; i++) s = crc16_byte(T, s, data[i]);
+  return (uint16_t)s;
+}
+
+int x3_write_frame_header(size_t num_samples, uint8_t id, size_t payload_len, uint16_t payload_crc,
+                          uint8_t header[20]) {
+  if (!header) return X3_ERR_INVALID_ARGUMENT;
+  memset(header, 0, 20);
+  header[0] = 0x78; header[1] = 0x33;
+  header[2] = id; header[3] = id;  // encoder.rs:131,135
+  header[4] = (uint8_t)(num_samples >> 8); header[5] = (uint8_t)num_samples;
+  header[6] = (uint8_t)(payload_len >> 8); header[7] = (uint8_t)payload_len;
+  const uint16_t hc = x3_crc16(header, 16);
+  header[16] = (uint8_t)(hc >> 8); header[17] = (uint8_t)hc;
+  header[18] = (uint8_t)(payload_crc >> 8); header[19] = (uint8_t)payload_crc;
+  return X3_OK;
+}
+
+int x3_read_frame_header(const uint8_t *b, size_t len, x3_frame_header *h) {
+  if (!b || !h) return X3_ERR_INVALID_ARGUMENT;
+  if (len < 20) return X3_ERR_FRAME_DECODE_UNEXPECTED_END;                                   // decoder.rs:70
+  if (x3_crc16(b, 16) != (uint16_t)((b[16] << 8) | b[17])) return X3_ERR_FRAME_HEADER_INVALID_HEADER_CRC;
+  if (((b[0] << 8) | b[1]) != (int)kFrameKey) return X3_ERR_FRAME_HEADER_INVALID_KEY;
+  h->source_id = b[2];
+  h->channels = b[3];
+  if (h->channels > 1) return X3_ERR_MORE_THAN_ONE_CHANNEL;
+  h->samples = (uint16_t)((b[4] << 8) | b[5]);
+  h->payload_len = (uint32_t)((b[6] << 8) | b[7]);
+  if (h->payload_len >= kFrameMaxLength) return X3_ERR_FRAME_LENGTH;
+  h->payload_crc = (uint16_t)((b[18] << 8) | b[19]);
+  return X3_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// encode
+// ------------------------------------------------------------------------------------------------
+int x3_encode_device(const int16_t *d_pcm, size_t n_samples, const x3_params *p, uint8_t *d_out, size_t out_cap,
+                     size_t *out_len, x3_stats *stats, void *cuda_stream) {
+  Derived d;
+  int rc = derive(p, &d);
+  if (rc) return rc;
+  if (!out_len || (n_samples && (!d_pcm || !d_out))) return X3_ERR_INVALID_ARGUMENT;
+  *out_len = 0;
+  if (stats) memset(stats, 0, sizeof *stats);
+  tl_ms[0] = tl_ms[1] = tl_ms[2] = tl_ms[3] = 0.f;
+  if (n_samples == 0) return X3_OK;
+  if (((uintptr_t)d_pcm & 1u) != 0) return X3_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  DeviceState *ds;
+  if ((rc = device_state(&ds))) return rc;
+  unsigned long long *host_res;
+  if ((rc = pinned(&host_res))) return rc;
+
+  const unsigned long long nf = (n_samples + d.P.spf - 1) / d.P.spf;
+  if (nf > 0xfffffff0ull) return X3_ERR_UNSUPPORTED_PARAMS;
+  const size_t ws_bytes = 128 + 8 * (size_t)nf;
+  unsigned char *ws = nullptr;
+  CU(cudaMallocAsync(&ws, ws_bytes, st));
+  cudaError_t e = cudaMemsetAsync(ws, 0, ws_bytes, st);
+  if (e != cudaSuccess) { cudaFreeAsync(ws, st); return cuda_fail(e, "cudaMemsetAsync"); }
+
+  EncodeArgs a;
+  a.pcm = d_pcm;
+  a.n_samples = n_samples;
+  a.out = d_out;
+  a.out_cap = out_cap;
+  a.P = d.P;
+  a.n_frames = (uint32_t)nf;
+  a.max_blocks = d.max_blocks;
+  a.out_words_cap = d.out_words_cap;
+  a.result = reinterpret_cast<unsigned long long *>(ws);        // 8 words
+  a.ticket = reinterpret_cast<unsigned int *>(ws + 64);
+  a.status = reinterpret_cast<unsigned long long *>(ws + 128);
+  a.crc_tables = ds->crc_dev;
+
+  const int occ = encode_occupancy(d.fast, d.smem);
+  unsigned long long grid = (unsigned long long)ds->sms * (unsigned)occ;
+  if (grid > nf) grid = nf;
+  Timer tm(st);
+  tm.start();
+  e = launch_encode(a, d.fast, (int)grid, d.smem, st);
+  tm.stop();
+  g_launches++;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(host_res, ws, 64, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFreeAsync(ws, st);
+  if (e != cudaSuccess) return cuda_fail(e, "encode_frames_kernel");
+  tl_ms[0] = tl_ms[2] = tm.ms();
+  *out_len = (size_t)host_res[0];
+  if (stats)
+    for (int k = 0; k < 6; k++) stats->samples_by_mode[k] = host_res[2 + k];
+  if (host_res[1]) return X3_ERR_BYTEWRITER_INSUFFICIENT_MEMORY;
+  return X3_OK;
+}
+
+int x3_encode_host(const int16_t *pcm, size_t n_samples, const x3_params *p, uint8_t *out, size_t out_cap,
+                   size_t *out_len, x3_stats *stats) {
+  Derived d;
+  int rc = derive(p, &d);
+  if (rc) return rc;
+  if (!out_len || (n_samples && (!pcm || !out))) return X3_ERR_INVALID_ARGUMENT;
+  *out_len = 0;
+  if (stats) memset(stats, 0, sizeof *stats);
+  if (n_samples == 0) return X3_OK;
+  cudaStream_t st = nullptr;
+  DeviceState *ds;
+  if ((rc = device_state(&ds))) return rc;
+  const size_t bound = x3_encode_bound(n_samples, p);
+  const size_t dcap = bound < out_cap ? bound : out_cap;  // never write more than the caller has room for
+  int16_t *d_pcm = nullptr;
+  uint8_t *d_out = nullptr;
+  CU(cudaMallocAsync(&d_pcm, n_samples * sizeof(int16_t), st));
+  cudaError_t e = cudaMallocAsync(&d_out, dcap ? dcap : 1, st);
+  if (e != cudaSuccess) { cudaFreeAsync(d_pcm, st); return cuda_fail(e, "cudaMallocAsync"); }
+  e = cudaMemcpyAsync(d_pcm, pcm, n_samples * sizeof(int16_t), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    rc = x3_encode_device(d_pcm, n_samples, p, d_out, dcap, out_len, stats, st);
+    if (rc == X3_OK || rc == X3_ERR_BYTEWRITER_INSUFFICIENT_MEMORY) {
+      const size_t ncopy = rc == X3_OK ? *out_len : 0;
+      if (ncopy) e = cudaMemcpyAsync(out, d_out, ncopy, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+  }
+  cudaFreeAsync(d_pcm, st);
+  cudaFreeAsync(d_out, st);
+  if (e != cudaSuccess) return cuda_fail(e, "x3_encode_host copies");
+  return rc;
+}
+
+int x3_encode_frame_host(const int16_t *pcm, size_t n_samples, const x3_params *p, uint8_t *out, size_t out_cap,
+                         size_t *out_len, x3_stats *stats) {
+  if (!p) return X3_ERR_INVALID_ARGUMENT;
+  if (n_samples == 0) return X3_ERR_REFERENCE_PANIC;  // wav[0], encoder.rs:189
+  if (n_samples > 65535) return X3_ERR_UNSUPPORTED_PARAMS;
+  // one frame = encode() with a frame length that covers the whole input
+  x3_params q = *p;
+  if (q.block_len == 0) return X3_ERR_INVALID_ARGUMENT;
+  q.blocks_per_frame = (uint32_t)((n_samples + q.block_len - 1) / q.block_len);
+  if ((unsigned long long)q.blocks_per_frame * q.block_len > 65535ull) q.blocks_per_frame = 65535u / q.block_len;
+  if ((unsigned long long)q.blocks_per_frame * q.block_len < n_samples) return X3_ERR_UNSUPPORTED_PARAMS;
+  return x3_encode_host(pcm, n_samples, &q, out, out_cap, out_len, stats);
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// The sequential header walk of decodefile.rs:105-126 on a host copy of the stream.
+// Returns the frames to decode and the condition that ended the walk (0 = clean stop).
+int host_walk(const uint8_t *s, size_t len, std::vector<FrameRec> &frames, unsigned long long *total_samples) {
+  size_t cursor = 0, remaining = len;
+  unsigned long long samples = 0;
+  for (;;) {
+    if (remaining <= 20) return X3_OK;                                 // :107-109
+    if (cursor + 20 > len) return X3_ERR_IO;
+    remaining -= 20;
+    x3_frame_header h;
+    int rc = x3_read_frame_header(s + cursor, 20, &h);                 // :112
+    cursor += 20;
+    if (rc) return rc;
+    if (remaining < h.payload_len) return X3_OK;                       // :114-116
+    FrameRec fr;
+    fr.pos = cursor - 20;
+    fr.out_off = samples;
+    fr.samples = h.samples;
+    fr.payload_len = h.payload_len;
+    fr.payload_crc = h.payload_crc;
+    fr.pad = 0;
+    frames.push_back(fr);
+    samples += h.samples;
+    *total_samples = samples;
+    if (h.payload_len > kReadBufferSize) return X3_OK;  // the frame itself reports InvalidPayloadLen (crc kernel)
+    remaining -= h.payload_len;
+    cursor += h.payload_len;
+  }
+}
+
+}  // namespace
+
+int x3_decode_device(const uint8_t *d_frames, size_t len, const x3_params *p, int16_t *d_pcm, size_t pcm_cap,
+                     size_t *n_out, x3_decode_result *res, void *cuda_stream) {
+  Derived d;
+  int rc = derive(p, &d);
+  if (rc == X3_ERR_UNSUPPORTED_PARAMS) {
+    // decode does not depend on the encoder-side limits (frame length comes from the headers)
+    if (!p || p->block_len == 0) return X3_ERR_INVALID_ARGUMENT;
+    d.P.block_len = p->block_len;
+    d.P.spf = 0;
+    for (int k = 0; k < 3; k++) { d.P.codes[k] = p->codes[k]; d.P.thresholds[k] = p->thresholds[k]; }
+    rc = X3_OK;
+  }
+  if (rc) return rc;
+  if (!n_out) return X3_ERR_INVALID_ARGUMENT;
+  *n_out = 0;
+  x3_decode_result local;
+  if (!res) res = &local;
+  memset(res, 0, sizeof *res);
+  res->first_bad_frame = UINT64_MAX;
+  tl_ms[0] = tl_ms[1] = tl_ms[2] = tl_ms[3] = 0.f;
+  if (len <= 20) return X3_OK;  // decodefile.rs:107-109
+  if (!d_frames || (!d_pcm && pcm_cap)) return X3_ERR_INVALID_ARGUMENT;
+  if (((uintptr_t)d_pcm & 1u) != 0) return X3_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  DeviceState *ds;
+  if ((rc = device_state(&ds))) return rc;
+  unsigned long long *host_res;
+  if ((rc = pinned(&host_res))) return rc;
+
+  const uint32_t n_tiles = (uint32_t)((len + kScanTileBytes - 1) / kScanTileBytes);
+  unsigned long long max_frames = len / 256 + 4096;
+  if (max_frames > len / 22 + 1) max_frames = len / 22 + 1;
+  // workspace layout
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_res = take(64), o_dres = take(64), o_tick = take(64), o_tiles = take(8 * (size_t)n_tiles);
+  const size_t zero_bytes = off;
+  const size_t o_frames = take(sizeof(FrameRec) * max_frames), o_fstat = take(sizeof(int) * max_frames);
+  unsigned char *ws = nullptr;
+  CU(cudaMallocAsync(&ws, off, st));
+  cudaError_t e = cudaMemsetAsync(ws, 0, zero_bytes, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(ws + o_dres, 0xff, 8, st);
+  auto fail = [&](cudaError_t ee, const char *what) { cudaFreeAsync(ws, st); return cuda_fail(ee, what); };
+  if (e != cudaSuccess) return fail(e, "cudaMemsetAsync");
+
+  ScanArgs sa;
+  sa.stream = d_frames;
+  sa.stream_len = len;
+  sa.frames = reinterpret_cast<FrameRec *>(ws + o_frames);
+  sa.max_frames = max_frames;
+  sa.tile_status = reinterpret_cast<unsigned long long *>(ws + o_tiles);
+  sa.ticket = reinterpret_cast<unsigned int *>(ws + o_tick);
+  sa.result = reinterpret_cast<unsigned long long *>(ws + o_res);
+  sa.crc_tables = ds->crc_dev;
+  sa.n_tiles = n_tiles;
+
+  DecodeArgs da;
+  da.stream = d_frames;
+  da.stream_len = len;
+  da.pcm = d_pcm;
+  da.pcm_cap = pcm_cap;
+  da.P = d.P;
+  da.frames = sa.frames;
+  da.n_frames = sa.result + 4;
+  da.max_frames = max_frames;
+  da.frame_status = reinterpret_cast<int *>(ws + o_fstat);
+  da.result = reinterpret_cast<unsigned long long *>(ws + o_dres);
+  da.crc_tables = ds->crc_dev;
+
+  Timer t_all(st), t_idx(st), t_crc(st), t_dec(st);
+  bool need_walk = (((uintptr_t)d_frames) & 15u) != 0;  // the scan uses 16-byte loads from the stream base
+  int walk_rc = X3_OK;
+  unsigned long long total_samples = 0, n_frames = 0;
+  t_all.start();
+  if (!need_walk) {
+    t_idx.start();
+    e = launch_scan(sa, st);
+    if (e == cudaSuccess) e = launch_chain_check(sa, st);
+    t_idx.stop();
+    g_launches += 2;
+    if (e != cudaSuccess) return fail(e, "scan_headers_kernel");
+    t_crc.start();
+    e = launch_crc(da, max_frames, st);
+    t_crc.stop();
+    if (e != cudaSuccess) return fail(e, "crc_frames_kernel");
+    t_dec.start();
+    e = launch_decode(da, max_frames, st);
+    t_dec.stop();
+    g_launches += 2;
+    if (e != cudaSuccess) return fail(e, "decode_frames_kernel");
+    t_all.stop();
+    e = cudaMemcpyAsync(host_res, ws + o_res, 64, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host_res + 8, ws + o_dres, 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(e, "decode (device index)");
+    if (host_res[2] != 0) need_walk = true;  // the table could not be proven equal to the reference's walk
+    n_frames = host_res[4];
+    total_samples = host_res[5];
+    tl_ms[0] = t_dec.ms();
+    tl_ms[1] = t_idx.ms();
+    tl_ms[2] = t_all.ms();
+    tl_ms[3] = t_crc.ms();
+  }
+  if (need_walk) {
+    // sequential host walk (rare: corrupt / foreign / unaligned streams)
+    res->used_host_walk = 1;
+    std::vector<uint8_t> host(len);
+    e = cudaMemcpyAsync(host.data(), d_frames, len, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(e, "host walk copy");
+    std::vector<FrameRec> frames;
+    walk_rc = host_walk(host.data(), len, frames, &total_samples);
+    n_frames = frames.size();
+    if (n_frames > max_frames) {
+      cudaFreeAsync(ws, st);
+      return X3_ERR_UNSUPPORTED_PARAMS;
+    }
+    host_res[4] = n_frames;
+    e = cudaMemcpyAsync(ws + o_res + 32, host_res + 4, 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && n_frames)
+      e = cudaMemcpyAsync(ws + o_frames, frames.data(), sizeof(FrameRec) * n_frames, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ws + o_dres, 0xff, 8, st);
+    if (e == cudaSuccess && n_frames) {
+      t_crc.start();
+      e = launch_crc(da, n_frames, st);
+      t_crc.stop();
+      t_dec.start();
+      if (e == cudaSuccess) e = launch_decode(da, n_frames, st);
+      t_dec.stop();
+      g_launches += 2;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host_res + 8, ws + o_dres, 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(e, "decode (host walk)");
+    if (n_frames) { tl_ms[0] = t_dec.ms(); tl_ms[3] = t_crc.ms(); tl_ms[2] = tl_ms[0] + tl_ms[3]; }
+  }
+
+  // ---- what the reference would have reported ----
+  const unsigned long long first_bad = host_res[8];
+  int ret = walk_rc;
+  unsigned long long good_frames = n_frames, good_samples = total_samples;
+  if (first_bad != ~0ull && first_bad < n_frames) {
+    int fstat = 0;
+    FrameRec fr;
+    e = cudaMemcpyAsync(&fstat, ws + o_fstat + sizeof(int) * first_bad, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(&fr, ws + o_frames + sizeof(FrameRec) * first_bad, sizeof(FrameRec), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(e, "decode status read-back");
+    good_frames = first_bad;
+    good_samples = fr.out_off;
+    res->first_bad_frame = first_bad;
+    res->first_bad_code = map_frame_error(fstat);
+    if (fstat == kDecErrOutOfBoundsInverse || fstat == kDecErrInvalidBpf) {
+      res->frame_errors = 1;  // decodefile.rs:130-134: counted, printed, decode stops, Ok(None)
+      ret = X3_OK;
+    } else {
+      ret = map_frame_error(fstat);  // payload CRC / payload length / capacity: propagated as Err
+    }
+  }
+  cudaFreeAsync(ws, st);
+  res->frames = good_frames;
+  res->samples = good_samples;
+  *n_out = (size_t)good_samples;
+  return ret;
+}
+
+int x3_decode_host(const uint8_t *frames, size_t len, const x3_params *p, int16_t *pcm, size_t pcm_cap, size_t *n_out,
+                   x3_decode_result *res) {
+  if (!n_out) return X3_ERR_INVALID_ARGUMENT;
+  *n_out = 0;
+  if (len <= 20) {
+    if (res) { memset(res, 0, sizeof *res); res->first_bad_frame = UINT64_MAX; }
+    return p ? X3_OK : X3_ERR_INVALID_ARGUMENT;
+  }
+  if (!frames || (!pcm && pcm_cap)) return X3_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = nullptr;
+  DeviceState *ds;
+  int rc = device_state(&ds);
+  if (rc) return rc;
+  uint8_t *d_in = nullptr;
+  int16_t *d_pcm = nullptr;
+  CU(cudaMallocAsync(&d_in, len + 16, st));
+  cudaError_t e = cudaMallocAsync(&d_pcm, (pcm_cap ? pcm_cap : 1) * sizeof(int16_t), st);
+  if (e != cudaSuccess) { cudaFreeAsync(d_in, st); return cuda_fail(e, "cudaMallocAsync"); }
+  e = cudaMemcpyAsync(d_in, frames, len, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    rc = x3_decode_device(d_in, len, p, d_pcm, pcm_cap, n_out, res, st);
+    if (rc != X3_ERR_CUDA && *n_out) {
+      e = cudaMemcpyAsync(pcm, d_pcm, *n_out * sizeof(int16_t), cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+  }
+  cudaFreeAsync(d_in, st);
+  cudaFreeAsync(d_pcm, st);
+  if (e != cudaSuccess) return cuda_fail(e, "x3_decode_host copies");
+  return rc;
+}
+
+int x3_decode_frame_host(const uint8_t *payload, size_t payload_len, const x3_params *p, int16_t *pcm, size_t pcm_cap,
+                         size_t samples, size_t *n_out) {
+  if (!payload || !p || !n_out) return X3_ERR_INVALID_ARGUMENT;
+  *n_out = 0;
+  if (payload_len < 2 || samples == 0) return X3_ERR_REFERENCE_PANIC;  // decoder.rs:42,47
+  if (payload_len >= kFrameMaxLength || samples > 65535) return X3_ERR_FRAME_LENGTH;
+  if (samples > pcm_cap) return X3_ERR_REFERENCE_PANIC;  // slice index out of range, decoder.rs:51
+  // wrap the payload in a frame so the stream path can be used
+  std::vector<uint8_t> buf(20 + payload_len);
+  x3_write_frame_header(samples, 1, payload_len, x3_crc16(payload, payload_len), buf.data());
+  memcpy(buf.data() + 20, payload, payload_len);
+  x3_decode_result r;
+  int rc = x3_decode_host(buf.data(), buf.size(), p, pcm, pcm_cap, n_out, &r);
+  if (rc == X3_OK && r.frame_errors) return r.first_bad_code;  // decode_frame itself returns the Err
+  return rc;
+}
+
+int x3_synth_device(int kind, uint32_t seed, uint32_t fs, uint64_t n0, uint64_t count, int16_t *d_out,
+                    void *cuda_stream) {
+  if ((kind != 1 && kind != 2 && kind != 4) || fs == 0 || (!d_out && count)) return X3_ERR_INVALID_ARGUMENT;
+  cudaError_t e = launch_synth(kind, seed, fs, n0, count, d_out, (cudaStream_t)cuda_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "synth_kernel");
+  g_launches++;
+  return X3_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+// x3_common.cuh -- shared definitions for the B200 X3 codec kernels.
+//
+// The per-thread codec logic (block classification, bit packing, bit parsing) lives in
+// __host__ __device__ functions so that tests/sim can run the exact same source on the CPU,
+// phase by phase, against the oracle before any GPU time is spent.  The cooperative parts
+// (scans, look-back, copies) are in the .cu files.
+#pragma once
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define X3_HD __host__ __device__ __forceinline__
+#define X3_D __device__ __forceinline__
+#else
+#define X3_HD inline
+#define X3_D inline
+#endif
+
+#if !defined(__CUDACC__)
+struct alignas(16) uint4 { uint32_t x, y, z, w; };  // host-only stand-in for the CUDA vector type (tests/sim)
+#endif
+
+namespace x3 {
+
+// ---- format constants (x3.rs:136-184) ------------------------------------------------------
+constexpr int kFrameHeaderLen = 20;        // FrameHeader::LENGTH, x3.rs:166
+constexpr uint32_t kFrameKey = 0x7833;     // "x3", x3.rs:169
+constexpr uint32_t kFrameMaxLength = 0x7fe0; // Frame::MAX_LENGTH, x3.rs:145
+constexpr int kMaxBlockLen = 60;           // Parameters::MAX_BLOCK_LENGTH, x3.rs:90
+constexpr uint32_t kReadBufferSize = 1024 * 24; // X3_READ_BUFFER_SIZE, decodefile.rs:44
+
+// inv_len of RICE0..3 (x3.rs:214,222,236,250) and table offsets (x3.rs:210,218,226,240)
+X3_HD uint32_t rice_inv_len(uint32_t code) { return code == 0 ? 16u : code == 1 ? 26u : code == 2 ? 44u : 60u; }
+X3_HD uint32_t rice_offset(uint32_t code) { return code == 0 ? 6u : code == 1 ? 11u : code == 2 ? 20u : 28u; }
+
+// ---- portable bit intrinsics ------------------------------------------------------------------
+X3_HD uint32_t clz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__clz((int)x);
+#else
+  return x ? (uint32_t)__builtin_clz(x) : 32u;
+#endif
+}
+X3_HD uint32_t bswap32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(x, 0, 0x0123);
+#else
+  return __builtin_bswap32(x);
+#endif
+}
+// (hi:lo) << s, upper word; s in [0,32]
+X3_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t s) {
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_lc(lo, hi, s);
+#else
+  if (s == 0) return hi;
+  if (s >= 32) return lo;
+  return (hi << s) | (lo >> (32 - s));
+#endif
+}
+// (hi:lo) >> s, lower word; s in [0,32]
+X3_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_rc(lo, hi, s);
+#else
+  if (s == 0) return lo;
+  if (s >= 32) return hi;
+  return (lo >> s) | (hi << (32 - s));
+#endif
+}
+X3_HD uint32_t shl_safe(uint32_t v, uint32_t s) { return s >= 32 ? 0u : v << s; }
+X3_HD uint32_t shr_safe(uint32_t v, uint32_t s) { return s >= 32 ? 0u : v >> s; }
+
+// zig-zag fold of the first difference: u = d<0 ? -2d-1 : 2d  (closed form of the `offset` indexing of
+// x3.rs:207-252, verified against the four tables by tests/test_oracle_golden.py)
+X3_HD uint32_t fold(int32_t d) { return ((uint32_t)d << 1) ^ (uint32_t)(d >> 31); }
+// INV_RICE_CODE[i], x3.rs:200-204
+X3_HD int32_t unfold(uint32_t i) { return (int32_t)(i >> 1) ^ -(int32_t)(i & 1u); }
+
+// ---- CRC-16/CCITT-FALSE (crc.rs) --------------------------------------------------------------
+// Table bank layout (uint16 entries), built on the host by x3_build_crc_tables():
+//   [0..4)   T_k[b] = b * x^(8k+16) mod P, k = 0..3       (slicing-by-4; T_0 is crc.rs:22-42)
+//   [4..6)   multiply by x^4096 (lo byte, hi byte)         (lane Horner step: 32 chunks of 16 bytes)
+//   [6..16)  multiply by x^(128*2^k), k = 0..4 (lo, hi)    (warp tree combine)
+constexpr int kCrcTables = 16;
+constexpr int kCrcTableEntries = kCrcTables * 256;
+
+// one 32-bit big-endian word (first stream byte in bits 31..24) through the CRC state
+X3_HD uint32_t crc16_word(const uint16_t *T, uint32_t s, uint32_t w) {
+  uint32_t v = (s << 16) ^ w;
+  return (uint32_t)T[768 + (v >> 24)] ^ (uint32_t)T[512 + ((v >> 16) & 0xff)] ^
+         (uint32_t)T[256 + ((v >> 8) & 0xff)] ^ (uint32_t)T[v & 0xff];
+}
+// one 16-bit big-endian halfword
+X3_HD uint32_t crc16_half(const uint16_t *T, uint32_t s, uint32_t h) {
+  uint32_t v = (s ^ h) & 0xffffu;
+  return (uint32_t)T[256 + (v >> 8)] ^ (uint32_t)T[v & 0xff];
+}
+X3_HD uint32_t crc16_byte(const uint16_t *T, uint32_t s, uint32_t b) {
+  return ((s << 8) & 0xffffu) ^ (uint32_t)T[((s >> 8) ^ b) & 0xff];
+}
+// multiply a 16-bit state by the constant whose (lo,hi) table pair starts at table index t
+X3_HD uint32_t crc16_mulc(const uint16_t *T, int t, uint32_t s) {
+  return (uint32_t)T[t * 256 + (s & 0xff)] ^ (uint32_t)T[(t + 1) * 256 + ((s >> 8) & 0xff)];
+}
+
+// frame header bytes 0..16 -> header CRC (encoder.rs:153); words are big-endian images of the bytes
+X3_HD uint32_t header_crc(const uint16_t *T, uint32_t id, uint32_t num_samples, uint32_t payload_len) {
+  uint32_t s = 0xffffu;
+  s = crc16_word(T, s, (kFrameKey << 16) | ((id & 0xff) << 8) | (id & 0xff));
+  s = crc16_word(T, s, ((num_samples & 0xffff) << 16) | (payload_len & 0xffff));
+  s = crc16_word(T, s, 0u);
+  s = crc16_word(T, s, 0u);
+  return s;
+}
+
+// ---- encoder parameters, preprocessed on the host ------------------------------------------------
+struct CodecParams {
+  uint32_t block_len;
+  uint32_t spf;            // samples per frame = block_len * blocks_per_frame
+  uint32_t codes[3];
+  uint32_t thresholds[3];
+};
+
+}  // namespace x3

@@ -1,0 +1,370 @@
+// x3_dec_core.cuh -- per-frame decoder logic (one thread = one frame).
+//
+// Replaces decoder::decode_frame (decoder.rs:36-58), decode_block (:132-145), the Rice / BFP / literal
+// block decoders (:147-235), BitReader (bitreader.rs:29-176) and the payload CRC check of
+// decodefile.rs:93-103.  Host+device so tests/sim can run the same source on the CPU.
+//
+// Two paths:
+//  * decode_frame_fast  -- Parameters::default() streams with frames of a multiple of 80 samples.  64-bit
+//    shifting bit window refilled once per three Rice codes, terminators by count-leading-zeros, output
+//    staged 160 bytes at a time so every lane writes whole 32-byte sectors.  The payload CRC is checked
+//    by a separate coalesced kernel (x3_decode.cu) before the frame is decoded, as decodefile.rs:93-103 does.  It never trusts a frame it cannot prove well formed: any
+//    zero run >= 32 bits, out-of-range Rice index or bad BFP header makes it give up ...
+//  * decode_frame_exact -- ... and the frame is decoded again by a literal restatement of the reference's
+//    word-structured BitReader, which reproduces its behaviour on malformed payloads bit for bit
+//    (short-tail refill, one-word look-ahead in count_zero_bits, zero fill past the end).  Also used for
+//    every frame the fast path does not cover (other Parameters, short last frame, unaligned output).
+#pragma once
+
+#include "x3_common.cuh"
+
+namespace x3 {
+
+enum : int {
+  kDecOk = 0,
+  kDecErrOutOfBoundsInverse = -2,  // X3Error::OutOfBoundsInverse
+  kDecErrPayloadLen = -9,          // X3Error::FrameHeaderInvalidPayloadLen
+  kDecErrPayloadCrc = -11,         // X3Error::FrameHeaderInvalidPayloadCRC
+  kDecErrInvalidBpf = -13,         // X3Error::FrameDecodeInvalidBPF
+  kDecErrNoSpace = -15,            // output capacity exceeded
+  kDecErrPanic = -104,             // the reference would panic (samples == 0, payload shorter than 2 bytes)
+  kDecRetryExact = 1               // fast path gave up; not an error
+};
+
+// ------------------------------------------------------------------------------------------------
+// Exact path: bitreader.rs restated over a byte pointer.
+// ------------------------------------------------------------------------------------------------
+struct ExactReader {
+  const uint8_t *a;
+  uint32_t len, idx;
+  uint32_t leading_word, rem_bit;
+
+  X3_HD void read_word(uint32_t at, uint32_t &word, uint32_t &nbytes) const {  // bitreader.rs:29-48
+    if (len - at >= 4u) {
+      word = ((uint32_t)a[at] << 24) | ((uint32_t)a[at + 1] << 16) | ((uint32_t)a[at + 2] << 8) | (uint32_t)a[at + 3];
+      nbytes = 4;
+    } else {
+      const uint32_t r = len - at;
+      uint32_t w = 0;
+      if (r >= 1) w |= (uint32_t)a[at] << 24;
+      if (r >= 2) w |= (uint32_t)a[at + 1] << 16;
+      if (r == 3) w |= (uint32_t)a[at + 2] << 8;
+      word = w;
+      nbytes = r;
+    }
+  }
+  X3_HD void init(const uint8_t *arr, uint32_t n) {  // bitreader.rs:65-74
+    a = arr; len = n;
+    uint32_t w, nb;
+    read_word(0, w, nb);
+    idx = nb; leading_word = w; rem_bit = nb * 8u;
+  }
+  X3_HD void get_next() {  // bitreader.rs:149-164
+    if (idx >= len) { leading_word = 0; rem_bit = 0; return; }
+    uint32_t w, nb;
+    read_word(idx, w, nb);
+    leading_word = w; idx += nb; rem_bit = nb * 8u;
+  }
+  X3_HD void inc_bits(uint32_t n) {  // bitreader.rs:77-92
+    if (n < rem_bit) {
+      leading_word = shl_safe(leading_word, n);
+      rem_bit -= n;
+    } else if (n > rem_bit) {
+      const uint32_t rem = n - rem_bit;
+      get_next();
+      rem_bit = 32u - rem;
+      leading_word = shl_safe(leading_word, rem);
+    } else {
+      get_next();
+    }
+  }
+  X3_HD uint32_t read_nbits(uint32_t n) {  // bitreader.rs:105-118
+    if (n <= rem_bit) {
+      const uint32_t r = leading_word >> (32u - n);
+      inc_bits(n);
+      return r;
+    }
+    const uint32_t rem = n - rem_bit;
+    uint32_t r = leading_word >> (32u - n);
+    inc_bits(rem_bit);
+    r |= leading_word >> (32u - rem);
+    inc_bits(rem);
+    return r;
+  }
+  X3_HD uint32_t count_zero_bits() {  // bitreader.rs:127-139
+    uint32_t count = clz32(leading_word);
+    if (count > rem_bit) {
+      if (idx < len) {
+        uint32_t w, nb;
+        read_word(idx, w, nb);
+        count = rem_bit + clz32(w);
+      } else {
+        count = rem_bit;
+      }
+    }
+    inc_bits(count);
+    return count;
+  }
+};
+
+// decoder.rs:36-58 with :132-235.  `out` gets `samples` values (2-byte stores).
+X3_HD int decode_frame_exact(const uint8_t *payload, uint32_t payload_len, int16_t *out, uint32_t samples,
+                             const CodecParams &P) {
+  if (payload_len < 2u || samples == 0u) return kDecErrPanic;
+  int32_t lw = (int16_t)(((uint32_t)payload[0] << 8) | (uint32_t)payload[1]);  // decoder.rs:42
+  uint32_t p_wav = 0;
+  out[p_wav++] = (int16_t)lw;
+  ExactReader br;
+  br.init(payload + 2, payload_len - 2u);
+  uint32_t remaining = samples - 1u;
+  while (remaining > 0u) {
+    const uint32_t bl = remaining < P.block_len ? remaining : P.block_len;  // decoder.rs:50
+    const uint32_t ftype = br.read_nbits(2);                                // decoder.rs:138
+    if (ftype == 0u) {                                                      // decode_bpf_block :209-235
+      const uint32_t nb = br.read_nbits(4) + 1u;
+      if (nb <= 5u) return kDecErrInvalidBpf;
+      if (nb == 16u) {
+        for (uint32_t i = 0; i < bl; i++) {
+          lw = (int16_t)br.read_nbits(16);
+          out[p_wav + i] = (int16_t)lw;
+        }
+      } else {
+        for (uint32_t i = 0; i < bl; i++) {
+          int32_t v = (int32_t)(br.read_nbits(nb) & 0xffffu);
+          if (v > (1 << (nb - 1u))) v -= (1 << nb);  // unsigned_to_i16, decoder.rs:198-207 (strictly greater)
+          lw = (int16_t)(lw + v);
+          out[p_wav + i] = (int16_t)lw;
+        }
+      }
+    } else {
+      const uint32_t code = P.codes[ftype - 1u];
+      const uint32_t inv_len = rice_inv_len(code);
+      if (ftype == 1u) {  // decode_ricecode_block_r1 :147-170
+        for (uint32_t i = 0; i < bl; i++) {
+          const uint32_t z = br.count_zero_bits();
+          br.read_nbits(1);
+          if (z >= inv_len) return kDecErrOutOfBoundsInverse;
+          lw = (int16_t)(lw + unfold(z));
+          out[p_wav + i] = (int16_t)lw;
+        }
+      } else {  // decode_ricecode_block_r2r3 :172-196
+        const uint32_t nb = ftype == 2u ? 2u : 4u;
+        const int32_t level = 1 << code;  // 1 << nsubs
+        for (uint32_t i = 0; i < bl; i++) {
+          const int32_t nz = (int16_t)br.count_zero_bits();
+          const int32_t r = (int16_t)br.read_nbits(nb);
+          const int32_t iv = (int16_t)(r + (int16_t)(level * (int16_t)(nz - 1)));
+          if (iv < 0 || (uint32_t)iv >= inv_len) return kDecErrOutOfBoundsInverse;
+          lw = (int16_t)(lw + unfold((uint32_t)iv));
+          out[p_wav + i] = (int16_t)lw;
+        }
+      }
+    }
+    remaining -= bl;
+    p_wav += bl;
+  }
+  return kDecOk;
+}
+
+X3_HD uint32_t crc16_bytes(const uint16_t *T, const uint8_t *d, uint32_t n) {
+  uint32_t s = 0xffffu;
+  for (uint32_t i = 0; i < n; i++) s = crc16_byte(T, s, d[i]);
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast path
+// ------------------------------------------------------------------------------------------------
+
+// Reader concept: uint32_t next() returns the next 32 payload bits (big-endian numeric, first stream byte
+// in bits 31..24).  It may return bytes that lie after the payload; decode_frame_fast checks at the end
+// that it never consumed a bit past the payload (the reference zero-fills there) and retries exactly if so.
+
+// Plain reader over memory through aligned 32-bit loads (host simulation and the device fallback).
+struct PlainWordReader {
+  const uint32_t *base;   // aligned word containing the payload's first byte
+  uint32_t k;             // next aligned word to load
+  uint32_t carry;         // previous loaded word (big-endian), for the 2-byte misaligned case
+  uint32_t sh;            // 32 when aligned, 16 when the payload starts in the middle of a word
+  uint32_t n_load;        // aligned words that may be loaded whole (all inside the stream buffer)
+  const uint8_t *end;     // end of the stream buffer
+
+  X3_HD uint32_t load(uint32_t i) const {
+    if (i < n_load) return bswap32(base[i]);
+    const uint8_t *p = reinterpret_cast<const uint8_t *>(base + i);  // word straddles / lies past the end
+    uint32_t w = 0;
+    for (int b = 0; b < 4; b++) w = (w << 8) | ((p + b < end) ? (uint32_t)p[b] : 0u);
+    return w;
+  }
+  X3_HD void init(const uint8_t *payload, const uint8_t *stream_end) {
+    end = stream_end;
+    const uintptr_t addr = (uintptr_t)payload;
+    base = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
+    const uintptr_t lim = (uintptr_t)stream_end & ~(uintptr_t)3;
+    n_load = lim > (uintptr_t)base ? (uint32_t)((lim - (uintptr_t)base) >> 2) : 0u;
+    if (addr & 2u) { sh = 16; carry = load(0); k = 1; }
+    else { sh = 32; carry = 0; k = 0; }
+  }
+  X3_HD void block_begin() {}
+  X3_HD uint32_t next() {
+    const uint32_t w = load(k);
+    k++;
+    const uint32_t v = funnel_l(w, carry, sh);
+    carry = w;
+    return v;
+  }
+};
+
+#if defined(__CUDA_ARCH__)
+#define X3_SHL64(v, s) ((v) << (s))
+#else
+#define X3_SHL64(v, s) ((s) >= 64 ? 0ull : ((v) << (s)))
+#endif
+
+struct BitWindow {
+  uint64_t bb;      // left-aligned bit buffer
+  int cnt;          // valid bits in bb
+  uint32_t words;   // words pulled from the reader
+  template <class Reader>
+  X3_HD void refill(Reader &rd) {
+    if (cnt <= 32) {
+      const uint32_t w = rd.next();
+      bb |= X3_SHL64((uint64_t)w, (unsigned)(32 - cnt));
+      cnt += 32;
+      words++;
+    }
+  }
+  X3_HD uint32_t hi() const { return (uint32_t)(bb >> 32); }
+  X3_HD uint32_t lo() const { return (uint32_t)bb; }
+  // the 32 bits that start s bits into the window (s <= 32)
+  X3_HD uint32_t peek(uint32_t s) const { return funnel_l(lo(), hi(), s); }
+  X3_HD void consume(uint32_t n) { bb = X3_SHL64(bb, n); cnt -= (int)n; }
+};
+
+constexpr uint32_t kFastGroup = 80;        // samples per staged flush (4 blocks of 20)
+constexpr uint32_t kStageWords = 44;       // per-thread staging stride in words (176 B: conflict-free LDS.128)
+
+// Fast-path eligibility of a frame (Parameters::default() is checked by the caller).
+X3_HD bool frame_fast_eligible(uint32_t samples, uint32_t payload_len, uintptr_t payload_addr, uintptr_t out_addr) {
+  return samples >= kFastGroup && samples % kFastGroup == 0u && payload_len >= 2u && (payload_len & 1u) == 0u &&
+         (payload_addr & 1u) == 0u && (out_addr & 31u) == 0u;
+}
+
+// one Rice code at offset `cum` of the window (decoder.rs:157-165 / :184-191 in closed form)
+#define X3_RICE_SAMPLE()                                                              \
+  {                                                                                   \
+    const uint32_t t = bw.peek(cum);                                                  \
+    const uint32_t z = clz32(t);                                                      \
+    const uint32_t r = shl_safe(t, z) >> (32u - nbk);                                 \
+    cum += z + nbk;                                                                   \
+    const uint32_t i = (uint32_t)((int32_t)r + level * ((int32_t)z - 1));             \
+    max_i = i > max_i ? i : max_i;                                                    \
+    lw += unfold(i);                                                                  \
+  }
+
+// Decode one frame.  `stage` = this thread's 44-word staging area (16-byte aligned).
+// Returns kDecOk or kDecRetryExact.
+template <class Reader>
+X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint32_t samples, uint32_t *stage) {
+  BitWindow bw;
+  bw.bb = 0; bw.cnt = 0; bw.words = 0;
+  rd.block_begin();
+  bw.refill(rd);
+  int32_t lw = (int32_t)(bw.hi() >> 16);   // first sample, decoder.rs:42 (only the low 16 bits of lw matter)
+  bw.consume(16);
+  uint32_t prev = (uint32_t)lw;            // last sample not yet written (low half of the next output word)
+  bool bad = false;
+
+  const uint32_t nblk = samples / 20u;     // the last block has 19 samples (encoder.rs:194)
+  uint4 *out4 = reinterpret_cast<uint4 *>(out);
+
+  for (uint32_t b = 0; b < nblk; b++) {
+    if (b) rd.block_begin();
+    const bool tail = (b == nblk - 1u);
+    uint32_t *st = stage + (b & 3u) * 10u;
+
+    bw.refill(rd);
+    const uint32_t hdr = bw.hi();
+    const uint32_t ftype = hdr >> 30;
+    if (ftype != 0u) {
+      // ---- Rice block: z zeros, then nbk bits of which the first is the terminator ----
+      bw.consume(2);
+      const uint32_t nbk = ftype == 1u ? 1u : (ftype == 2u ? 2u : 4u);          // decoder.rs:158,180
+      const int32_t level = ftype == 1u ? 1 : (ftype == 2u ? 2 : 8);            // 1<<nsubs of RICE1 / RICE3
+      const uint32_t inv_len = ftype == 1u ? 16u : (ftype == 2u ? 26u : 60u);   // x3.rs:214,222,250
+      uint32_t max_i = 0, cum = 0, cmax = 0;
+      // samples x0..x19; output words (prev,x0) (x1,x2) ... (x17,x18); x19 becomes prev.
+      // A valid code is at most 10 bits, so three codes are parsed per refill / consume.
+#pragma unroll
+      for (int i = 0; i < 20; i++) {
+        if (i % 3 == 0) { bw.refill(rd); cum = 0; }
+        if (i < 19 || !tail) {
+          X3_RICE_SAMPLE();
+          if ((i & 1) == 0) st[i >> 1] = (prev & 0xffffu) | ((uint32_t)lw << 16);
+          else prev = (uint32_t)lw;
+        }
+        if (i % 3 == 2 || i == 19) {
+          cmax = cum > cmax ? cum : cmax;
+          bw.consume(cum);
+        }
+      }
+      // out-of-range index (decoder.rs:161,187; includes every zero run the 32-bit peek cannot see the end of)
+      // or a group of codes longer than the 32 valid bits a refill guarantees -> let the exact path decide
+      if (max_i >= inv_len || cmax > 32u) bad = true;
+    } else {
+      const uint32_t nb = ((hdr >> 26) & 15u) + 1u;  // decoder.rs:211
+      bw.consume(6);
+      if (nb <= 5u) { bad = true; break; }           // FrameDecodeInvalidBPF, decoder.rs:213-216
+      if (nb == 16u) {
+        // ---- literal block: raw 16-bit samples ----
+        for (int j = 0; j < 10; j++) {
+          bw.refill(rd);
+          lw = (int32_t)(bw.hi() >> 16);
+          st[j] = (prev & 0xffffu) | ((uint32_t)lw << 16);
+          if (j < 9 || !tail) {
+            lw = (int32_t)(bw.hi() & 0xffffu);
+            prev = (uint32_t)lw;
+            bw.consume(32);
+          } else {
+            bw.consume(16);
+          }
+        }
+      } else {
+        // ---- BFP block: nb-bit two's complement differences (decoder.rs:224-231) ----
+        const int32_t half = 1 << (nb - 1u), full = 1 << nb;
+        for (int j = 0; j < 10; j++) {
+          bw.refill(rd);
+          int32_t v = (int32_t)(bw.hi() >> (32u - nb));
+          if (v > half) v -= full;                    // unsigned_to_i16: strictly greater, decoder.rs:203
+          lw += v;
+          st[j] = (prev & 0xffffu) | ((uint32_t)lw << 16);
+          if (j < 9 || !tail) {
+            v = (int32_t)(bw.peek(nb) >> (32u - nb));
+            if (v > half) v -= full;
+            lw += v;
+            prev = (uint32_t)lw;
+            bw.consume(2u * nb);
+          } else {
+            bw.consume(nb);
+          }
+        }
+      }
+    }
+    if (bad) break;
+    // ---- every fourth block: 160 staged bytes -> five whole sectors of the output ----
+    if ((b & 3u) == 3u) {
+      const uint4 *s4 = reinterpret_cast<const uint4 *>(stage);
+      uint4 *o = out4 + (size_t)(b >> 2) * 10u;
+#pragma unroll
+      for (int q = 0; q < 10; q++) o[q] = s4[q];
+    }
+  }
+  if (bad) return kDecRetryExact;
+  // bits consumed must lie inside the payload (the reference zero-fills past the end; we may have read
+  // the next frame's bytes there instead)
+  const long long used = 32ll * (long long)bw.words - (long long)bw.cnt;
+  if (used > 8ll * (long long)payload_len) return kDecRetryExact;
+  return kDecOk;
+}
+
+}  // namespace x3

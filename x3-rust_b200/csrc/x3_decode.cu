@@ -1,0 +1,417 @@
+// x3_decode.cu -- frame index, payload CRC and frame decode kernels for sm_100a.
+//
+// Decode of a device-resident frame stream is three stream-ordered steps, no host round trip:
+//   1. scan_headers_kernel  -- finds every frame header (key 'x3' + header CRC + field checks of
+//      decoder.rs:69-118) at even offsets, orders them with a single-pass decoupled look-back and writes
+//      the dense frame table (position, sample offset); check_chain_kernel then proves the table is
+//      exactly the header -> payload_len -> next header walk of decodefile.rs:105-126.  Anything it cannot
+//      prove (false candidate, corrupt header, odd payload length) raises a flag and the API falls
+//      back to the sequential host walk, which reproduces the reference's error behaviour.
+//   2. crc_frames_kernel    -- one warp per frame, coalesced 16-byte chunks, chunk CRCs combined with
+//      multiply-by-x^n tables (same scheme as the encoder): decodefile.rs:93-103.
+//   3. decode_frames_kernel -- one thread per frame (frames are independent, blocks inside a frame are
+//      not): x3_dec_core.cuh.  Every lane streams its own payload through a private 128-byte
+//      shared-memory ring filled by cp.async one block ahead, and writes whole 32-byte sectors.
+#include <cuda_runtime.h>
+
+#include "x3_dec_core.cuh"
+#include "x3_kernels.h"
+#include "x3_lookback.cuh"
+
+namespace x3 {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// 1. frame index
+// ------------------------------------------------------------------------------------------------
+constexpr int kScanCap = 512;                 // candidates per 64 KiB tile before falling back
+constexpr int kCountShift = 38;               // look-back value = (frames << 38) | samples
+
+struct Cand {
+  uint32_t off;       // byte offset inside the tile
+  uint32_t samples;
+  uint32_t payload_len;
+  uint32_t payload_crc;
+};
+
+// decoder::read_frame_header checks (decoder.rs:69-118) on 20 bytes at p (p is 2-byte aligned)
+__device__ bool header_valid(const uint8_t *p, const uint16_t *T, Cand &c) {
+  const uint16_t *h = reinterpret_cast<const uint16_t *>(p);
+  uint32_t w[10];
+#pragma unroll
+  for (int i = 0; i < 10; i++) {
+    const uint32_t v = h[i];
+    w[i] = ((v & 0xff) << 8) | (v >> 8);  // big-endian halfword
+  }
+  uint32_t s = 0xffffu;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s = crc16_half(T, s, w[i]);
+  if (s != w[8]) return false;                    // FrameHeaderInvalidHeaderCRC
+  if (w[0] != kFrameKey) return false;            // FrameHeaderInvalidKey
+  if ((w[1] & 0xff) > 1u) return false;           // MoreThanOneChannel
+  if (w[3] >= kFrameMaxLength) return false;      // FrameLength
+  c.samples = w[2];
+  c.payload_len = w[3];
+  c.payload_crc = w[9];
+  return true;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_headers_kernel(const ScanArgs a) {
+  __shared__ uint16_t s_T[512];  // T_0, T_1 of the CRC bank are enough for halfword updates
+  __shared__ Cand s_cand[kScanCap];
+  __shared__ uint32_t s_rank[kScanCap];
+  __shared__ unsigned int s_count;
+  __shared__ unsigned int s_tile;
+  __shared__ unsigned long long s_base;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 512; i += kScanThreads) s_T[i] = a.crc_tables[i];
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) { s_tile = atomicAdd(a.ticket, 1u); s_count = 0; }
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    if (tile >= a.n_tiles) break;
+    const unsigned long long t0 = (unsigned long long)tile * kScanTileBytes;
+    const unsigned long long t1 = t0 + kScanTileBytes < a.stream_len ? t0 + kScanTileBytes : a.stream_len;
+
+    // ---- candidates: halfword 'x','3' at an even offset with a valid header behind it ----
+    for (unsigned long long o = t0 + (unsigned long long)tid * 16u; o < t1; o += (unsigned long long)kScanThreads * 16u) {
+      uint32_t q[4] = {0u, 0u, 0u, 0u};
+      if (o + 16u <= a.stream_len) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(a.stream + o);
+        q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w;
+      } else {
+        for (unsigned long long b = o; b < a.stream_len; b++) q[(b - o) >> 2] |= (uint32_t)a.stream[b] << (8u * ((b - o) & 3u));
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint32_t x = q[j] ^ 0x33783378u;  // bytes 78 33 in memory order
+        if (((x - 0x00010001u) & ~x & 0x80008000u) == 0u) continue;  // no zero halfword
+#pragma unroll
+        for (int hsel = 0; hsel < 2; hsel++) {
+          if (((x >> (16 * hsel)) & 0xffffu) != 0u) continue;
+          const unsigned long long p = o + 4u * j + 2u * hsel;
+          if (p + kFrameHeaderLen > a.stream_len) continue;
+          Cand c;
+          if (!header_valid(a.stream + p, s_T, c)) continue;
+          c.off = (uint32_t)(p - t0);
+          const unsigned int idx = atomicAdd(&s_count, 1u);
+          if (idx < kScanCap) s_cand[idx] = c;
+        }
+      }
+    }
+    __syncthreads();
+    const uint32_t cnt = s_count < (unsigned)kScanCap ? s_count : (unsigned)kScanCap;
+    if (tid == 0 && s_count > (unsigned)kScanCap) atomicOr(a.result + 2, 1ull);
+
+    // ---- order inside the tile (rank sort; a tile holds about a dozen frames) ----
+    unsigned long long tile_samples = 0;
+    for (uint32_t j = tid; j < cnt; j += kScanThreads) {
+      uint32_t r = 0;
+      const uint32_t mine = s_cand[j].off;
+      for (uint32_t m = 0; m < cnt; m++) r += s_cand[m].off < mine;
+      s_rank[r] = j;
+    }
+    __syncthreads();
+
+    // ---- frame ordinal and sample offset of the tile's first frame: look-back over tiles ----
+    if (tid < 32) {
+      for (uint32_t j = tid; j < cnt; j += 32) tile_samples += s_cand[j].samples;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) tile_samples += __shfl_xor_sync(0xffffffffu, tile_samples, d);
+      const unsigned long long own = ((unsigned long long)cnt << kCountShift) | tile_samples;
+      if (tid == 0) st_status(a.tile_status + tile, (tile == 0 ? kFlagPrefix : kFlagAgg) | own);
+      const unsigned long long excl = lookback_exclusive(a.tile_status, tile, own);
+      if (tid == 0) {
+        s_base = excl;
+        if (tile == a.n_tiles - 1) {
+          const unsigned long long tot = excl + own;
+          a.result[0] = tot >> kCountShift;
+          a.result[1] = tot & ((1ull << kCountShift) - 1ull);
+        }
+      }
+    }
+    __syncthreads();
+    const unsigned long long base_count = s_base >> kCountShift;
+    const unsigned long long base_samples = s_base & ((1ull << kCountShift) - 1ull);
+    for (uint32_t r = tid; r < cnt; r += kScanThreads) {
+      const Cand c = s_cand[s_rank[r]];
+      unsigned long long before = 0;
+      for (uint32_t m = 0; m < r; m++) before += s_cand[s_rank[m]].samples;
+      const unsigned long long ord = base_count + r;
+      if (ord < a.max_frames) {
+        FrameRec fr;
+        fr.pos = t0 + c.off;
+        fr.out_off = base_samples + before;
+        fr.samples = c.samples;
+        fr.payload_len = c.payload_len;
+        fr.payload_crc = c.payload_crc;
+        fr.pad = 0;
+        a.frames[ord] = fr;
+      } else {
+        atomicOr(a.result + 2, 1ull);
+      }
+    }
+  }
+}
+
+// The table is the reference's walk iff it starts at 0, every frame ends where the next begins, and
+// nothing but a short tail (<= 20 bytes, decodefile.rs:107-109) or a truncated final frame
+// (decodefile.rs:114-116) follows.
+__global__ void check_chain_kernel(const ScanArgs a) {
+  const unsigned long long n = a.result[0];
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  if (i == 0) {
+    if (n == 0) {
+      a.result[4] = 0;
+      a.result[5] = 0;
+      if (a.stream_len > (unsigned long long)kFrameHeaderLen) atomicOr(a.result + 2, 1ull);
+    } else if (n <= a.max_frames && a.frames[0].pos != 0) {
+      atomicOr(a.result + 2, 1ull);
+    }
+    if (n > a.max_frames) atomicOr(a.result + 2, 1ull);
+  }
+  if (n > a.max_frames) return;
+  for (unsigned long long k = i; k < n; k += stride) {
+    const FrameRec fr = a.frames[k];
+    const unsigned long long end = fr.pos + kFrameHeaderLen + fr.payload_len;
+    if (k + 1 < n) {
+      if (a.frames[k + 1].pos != end) atomicOr(a.result + 2, 1ull);
+    } else {
+      // final counts for the kernels that follow (result[4] frames, result[5] samples)
+      if (end > a.stream_len) {
+        a.result[4] = n - 1;  // truncated final frame: the reference stops cleanly before it
+        a.result[5] = a.result[1] - fr.samples;
+      } else {
+        a.result[4] = n;
+        a.result[5] = a.result[1];
+        if (a.stream_len - end > (unsigned long long)kFrameHeaderLen) atomicOr(a.result + 2, 1ull);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2. payload CRC, one warp per frame
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t load_be32_2aligned(const uint8_t *p) {
+  // p is 2-byte aligned
+  const uint16_t *h = reinterpret_cast<const uint16_t *>(p);
+  const uint32_t a = h[0], b = h[1];
+  return ((a & 0xff) << 24) | ((a >> 8) << 16) | ((b & 0xff) << 8) | (b >> 8);
+}
+
+__global__ void __launch_bounds__(256) crc_frames_kernel(const DecodeArgs a) {
+  __shared__ uint16_t s_T[kCrcTableEntries];
+  for (int i = threadIdx.x; i < kCrcTableEntries; i += blockDim.x) s_T[i] = a.crc_tables[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const unsigned long long n = *a.n_frames < a.max_frames ? *a.n_frames : a.max_frames;
+  const unsigned long long warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+  for (unsigned long long f = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; f < n; f += warps) {
+    const FrameRec fr = a.frames[f];
+    int status = kDecOk;
+    const unsigned long long pend = fr.pos + kFrameHeaderLen + fr.payload_len;
+    if (pend > a.stream_len) {
+      status = kDecErrPanic;  // never produced by the index (truncated frames are dropped); defensive
+    } else if (fr.payload_len > kReadBufferSize) {
+      status = kDecErrPayloadLen;  // decodefile.rs:118-121
+    } else {
+      const uint8_t *pl = a.stream + fr.pos + kFrameHeaderLen;
+      const uint32_t len = fr.payload_len;
+      uint32_t s;
+      if (((uintptr_t)pl & 1u) || (len & 1u)) {
+        s = 0xffffu;  // odd placement (foreign stream): bytewise
+        if (lane == 0) s = crc16_bytes(s_T, pl, len);
+        s = __shfl_sync(0xffffffffu, s, 0);
+      } else {
+        const uint32_t m = len >> 4;  // whole 16-byte chunks
+        uint32_t h = 0;
+        if (m > (uint32_t)lane) {
+          for (int i = (int)((m - 1u - lane) >> 5); i >= 0; i--) {
+            const uint32_t c = m - 1u - (32u * (uint32_t)i + lane);
+            const uint8_t *q = pl + 16u * c;
+            uint32_t cs = c == 0 ? 0xffffu : 0u;
+            if (((uintptr_t)q & 3u) == 0) {
+              const uint32_t *q4 = reinterpret_cast<const uint32_t *>(q);
+#pragma unroll
+              for (int w = 0; w < 4; w++) cs = crc16_word(s_T, cs, bswap32(q4[w]));
+            } else {
+#pragma unroll
+              for (int w = 0; w < 4; w++) cs = crc16_word(s_T, cs, load_be32_2aligned(q + 4 * w));
+            }
+            h = crc16_mulc(s_T, 4, h) ^ cs;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+          const uint32_t o = __shfl_down_sync(0xffffffffu, h, 1 << k);
+          h ^= crc16_mulc(s_T, 6 + 2 * k, o);
+        }
+        s = m ? h : 0xffffu;
+        if (lane == 0) {
+          const uint8_t *q = pl + 16u * m;
+          const uint32_t rem = len & 15u;
+          uint32_t done = 0;
+          for (; done + 4u <= rem; done += 4u) s = crc16_word(s_T, s, load_be32_2aligned(q + done));
+          if (rem & 2u) {
+            const uint32_t v = *reinterpret_cast<const uint16_t *>(q + done);
+            s = crc16_half(s_T, s, ((v & 0xff) << 8) | (v >> 8));
+          }
+        }
+        s = __shfl_sync(0xffffffffu, s, 0);
+      }
+      if ((s & 0xffffu) != fr.payload_crc) status = kDecErrPayloadCrc;  // decodefile.rs:97-100
+    }
+    if (lane == 0) a.frame_status[f] = status;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3. decode, one thread per frame
+// ------------------------------------------------------------------------------------------------
+constexpr int kRingWords = 36;  // 32 used (8 chunks of 16 B) + 4 pad: stride 144 B spreads lanes over banks
+
+// Per-lane reader: the lane's payload streams through its own shared-memory ring, filled by cp.async
+// at least one block ahead of consumption (a block consumes at most 41 bytes).
+struct RingReader {
+  const unsigned char *g0;   // 16-byte aligned global address of chunk 0 (contains the payload's first byte)
+  uint32_t *ring;
+  const unsigned char *end;  // end of the stream buffer
+  uint32_t issued;           // chunks issued so far
+  uint32_t n_async;          // chunks [0, n_async) lie wholly inside the stream buffer
+  uint32_t k, carry, sh;
+
+  __device__ __forceinline__ void issue_to(uint32_t want) {
+    while (issued < want) {
+      uint32_t *slot = ring + (issued & 7u) * 4u;
+      const unsigned char *src = g0 + 16ull * issued;
+      if (issued < n_async) {
+        cp_async16(slot, src);
+      } else {
+        for (int w = 0; w < 4; w++) {
+          uint32_t v = 0;
+          for (int b = 0; b < 4; b++)
+            if (src + 4 * w + b < end) v |= (uint32_t)src[4 * w + b] << (8 * b);
+          slot[w] = v;
+        }
+      }
+      issued++;
+    }
+    cp_async_commit();
+  }
+  __device__ __forceinline__ void start(const uint8_t *payload, const uint8_t *stream_end, uint32_t *ring_) {
+    ring = ring_;
+    end = stream_end;
+    g0 = reinterpret_cast<const unsigned char *>((uintptr_t)payload & ~(uintptr_t)15);
+    const uintptr_t span = (uintptr_t)stream_end - (uintptr_t)g0;
+    n_async = (uint32_t)(span >> 4 > 0xffffffffull ? 0xffffffffull : span >> 4);
+    issued = 0;
+    const uint32_t off0 = (uint32_t)((uintptr_t)payload & 15u);
+    k = off0 >> 2;
+    issue_to((4u * k + 112u + 15u) >> 4);
+    cp_async_wait_all();
+    if (off0 & 2u) { sh = 16; carry = bswap32(ring[k & 31u]); k++; }
+    else { sh = 32; carry = 0; }
+  }
+  __device__ __forceinline__ void block_begin() {
+    issue_to((4u * k + 112u + 15u) >> 4);
+    cp_async_wait_1();
+  }
+  __device__ __forceinline__ uint32_t next() {
+    const uint32_t w = bswap32(ring[k & 31u]);
+    k++;
+    const uint32_t v = funnel_l(w, carry, sh);
+    carry = w;
+    return v;
+  }
+};
+
+__global__ void __launch_bounds__(kDecThreads) decode_frames_kernel(const DecodeArgs a) {
+  __shared__ __align__(16) uint32_t s_ring[kDecThreads * kRingWords];
+  __shared__ __align__(16) uint32_t s_stage[kDecThreads * kStageWords];
+  const int tid = threadIdx.x;
+  const unsigned long long n = *a.n_frames < a.max_frames ? *a.n_frames : a.max_frames;
+  const bool dflt = a.P.block_len == 20 && a.P.codes[0] == 0 && a.P.codes[1] == 1 && a.P.codes[2] == 3;
+  const uint8_t *stream_end = a.stream + a.stream_len;
+  for (unsigned long long base = (unsigned long long)blockIdx.x * kDecThreads; base < n;
+       base += (unsigned long long)gridDim.x * kDecThreads) {
+    const unsigned long long i = base + tid;
+    if (i >= n) continue;
+    const FrameRec fr = a.frames[i];
+    int status = a.frame_status[i];  // set by crc_frames_kernel
+    if (status == kDecOk) {
+      if (fr.samples == 0u || fr.payload_len < 2u) {
+        status = kDecErrPanic;
+      } else if (fr.out_off + fr.samples > a.pcm_cap) {
+        status = kDecErrNoSpace;
+      } else {
+        const uint8_t *pl = a.stream + fr.pos + kFrameHeaderLen;
+        int16_t *out = a.pcm + fr.out_off;
+        int r = kDecRetryExact;
+        if (dflt && frame_fast_eligible(fr.samples, fr.payload_len, (uintptr_t)pl, (uintptr_t)out)) {
+          RingReader rd;
+          rd.start(pl, stream_end, s_ring + tid * kRingWords);
+          r = decode_frame_fast(rd, fr.payload_len, out, fr.samples, s_stage + tid * kStageWords);
+          cp_async_wait_all();
+        }
+        if (r == kDecRetryExact) r = decode_frame_exact(pl, fr.payload_len, out, fr.samples, a.P);
+        status = r;
+      }
+    }
+    a.frame_status[i] = status;
+    if (status != kDecOk) atomicMin(a.result, i);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_scan(const ScanArgs &a, cudaStream_t stream) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int grid = sms * 6;
+  if ((uint32_t)grid > a.n_tiles) grid = (int)a.n_tiles;
+  if (grid < 1) grid = 1;
+  scan_headers_kernel<<<grid, kScanThreads, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_chain_check(const ScanArgs &a, cudaStream_t stream) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  check_chain_kernel<<<sms * 4, 256, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_crc(const DecodeArgs &a, unsigned long long n_frames_hint, cudaStream_t stream) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (n_frames_hint < 1) n_frames_hint = 1;
+  unsigned long long g = (n_frames_hint * 32ull + 255ull) / 256ull;  // one warp per frame
+  const unsigned long long cap = (unsigned long long)sms * 8ull;
+  if (g > cap) g = cap;
+  crc_frames_kernel<<<(unsigned)g, 256, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_decode(const DecodeArgs &a, unsigned long long n_frames_hint, cudaStream_t stream) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (n_frames_hint < 1) n_frames_hint = 1;
+  {
+    unsigned long long g = (n_frames_hint + kDecThreads - 1) / kDecThreads;
+    const unsigned long long cap = (unsigned long long)sms * 16ull;
+    if (g > cap) g = cap;
+    decode_frames_kernel<<<(unsigned)g, kDecThreads, 0, stream>>>(a);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace x3

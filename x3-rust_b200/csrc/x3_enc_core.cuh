@@ -1,0 +1,271 @@
+// x3_enc_core.cuh -- per-block encoder logic (one thread = one block of <= 60 samples).
+//
+// Replaces, per block: encoder::diff (encoder.rs:222-225), x3_encode_block (encoder.rs:289-315),
+// encode_rice_block (:233-267), encode_bfp_block (:269-276), encode_literal (:278-285) and the
+// BitPacker (bitpacker.rs:142-163).  Host+device so that tests/sim can run it on the CPU.
+//
+// Bit layout.  A frame payload is one MSB-first bit string (bitpacker.rs).  The kernel keeps it in
+// shared memory as a byte image addressed as 32-bit words.  A block whose bit range is
+// [o, o+n) writes every word it owns exactly once:
+//   * words that start inside the block and end inside it  -> plain store while packing
+//   * the word holding its first bit when o % 32 != 0       -> "head" partial, published to Hs[b]
+//   * the word holding its last bit when (o+n) % 32 != 0    -> "tail" partial Ts[b]; after a barrier
+//     the owner ORs in the heads of the following blocks that start in that word (at most two when
+//     block_len is 20; a loop handles shorter blocks).
+// No atomics and no pre-zeroing are needed; every output word has exactly one writer.
+#pragma once
+
+#include "x3_common.cuh"
+
+namespace x3 {
+
+enum BlockKind : uint32_t { kRice = 0, kBfp = 1, kLiteral = 2 };
+
+struct BlockMode {
+  uint32_t kind;   // BlockKind
+  uint32_t k;      // Rice: number of suffix bits (RiceCode.nsubs); BFP: bits per sample - 1 (num_bits)
+  uint32_t hdr;    // header value: ftype+1 in 2 bits (encoder.rs:250) or num_bits / 15 in 6 bits (:270,:280)
+  uint32_t stat;   // index into stats[6] (encoder.rs:266,275,284)
+};
+
+// The selection rule of encoder.rs:304-314 + :241-247.  It is a threshold rule on max|d|.
+X3_HD BlockMode classify(uint32_t max_abs, const CodecParams &P) {
+  BlockMode m;
+  if (max_abs <= P.thresholds[2]) {
+    uint32_t ftype = (max_abs > P.thresholds[0]) + (max_abs > P.thresholds[1]) + (max_abs > P.thresholds[2]);
+    m.kind = kRice;
+    m.k = P.codes[ftype];
+    m.hdr = ftype + 1;
+    m.stat = m.k;
+  } else {
+    uint32_t nb = 32u - clz32(max_abs);  // count_bits, encoder.rs:229-231
+    if (nb >= 15) {
+      m.kind = kLiteral; m.k = 15; m.hdr = 15; m.stat = 5;
+    } else {
+      m.kind = kBfp; m.k = nb; m.hdr = nb; m.stat = 4;
+    }
+  }
+  return m;
+}
+
+// bits a block of `len` samples occupies, given its mode and (for Rice) the sum of u>>k
+X3_HD uint32_t block_bits(const BlockMode &m, uint32_t len, uint32_t sum_q) {
+  if (m.kind == kRice) return 2u + len * (m.k + 1u) + sum_q;
+  if (m.kind == kBfp) return 6u + len * (m.k + 1u);
+  return 6u + len * 16u;
+}
+
+// MSB-first bit sink over the shared-memory byte image (see file comment).
+struct BitSink {
+  uint64_t acc;
+  uint32_t cnt;       // valid low bits of acc not yet stored
+  uint32_t *dst;      // where the next completed word goes
+  uint32_t *nxt;      // the word after that
+  uint32_t *head;     // Hs[b]
+
+  X3_HD void init(uint32_t bit_off, uint32_t *out_words, uint32_t *head_slot) {
+    acc = 0;
+    cnt = bit_off & 31u;
+    head = head_slot;
+    uint32_t *w = out_words + (bit_off >> 5);
+    nxt = w + 1;
+    if (cnt) {
+      dst = head_slot;
+    } else {
+      dst = w;
+      *head_slot = 0u;
+    }
+  }
+  // append the low n bits of v (v < 2^n, n <= 32)
+  X3_HD void put(uint32_t v, uint32_t n) {
+    acc = (acc << n) | (uint64_t)v;
+    cnt += n;
+  }
+  // store one completed word if there is one (call often enough that cnt never exceeds 64)
+  X3_HD void flush() {
+    if (cnt >= 32u) {
+      cnt -= 32u;
+      *dst = bswap32((uint32_t)(acc >> cnt));
+      dst = nxt;
+      nxt = nxt + 1;
+    }
+  }
+  // end of block: returns the tail partial word image (0 if none) and sets has_tail
+  X3_HD uint32_t finish(bool &has_tail) {
+    flush();
+    has_tail = false;
+    if (cnt == 0u) return 0u;
+    uint32_t img = bswap32((uint32_t)(acc << (32u - cnt)));
+    if (dst == head) {  // never completed a word and started mid-word: all bits belong to a predecessor's word
+      *head = img;
+      return 0u;
+    }
+    has_tail = true;
+    return img;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Generic block path: any block_len <= 60, any codes / thresholds.  Reads the samples three times
+// from (shared) memory; used for non-default Parameters and for short tail blocks.
+// `s` points at the frame's samples, block covers s[start .. start+len), predecessor s[start-1].
+// ---------------------------------------------------------------------------------------------
+X3_HD BlockMode block_measure_generic(const int16_t *s, uint32_t start, uint32_t len, const CodecParams &P,
+                                      uint32_t &nbits) {
+  uint32_t maxu = 0;
+  int32_t prev = s[start - 1];
+  for (uint32_t i = 0; i < len; i++) {
+    int32_t x = s[start + i];
+    uint32_t u = fold(x - prev);
+    prev = x;
+    maxu = u > maxu ? u : maxu;
+  }
+  BlockMode m = classify((maxu + 1u) >> 1, P);
+  uint32_t sum_q = 0;
+  if (m.kind == kRice) {
+    prev = s[start - 1];
+    for (uint32_t i = 0; i < len; i++) {
+      int32_t x = s[start + i];
+      sum_q += fold(x - prev) >> m.k;
+      prev = x;
+    }
+  }
+  nbits = block_bits(m, len, sum_q);
+  return m;
+}
+
+X3_HD void block_pack_generic(const int16_t *s, uint32_t start, uint32_t len, const BlockMode &m, BitSink &sink) {
+  int32_t prev = s[start - 1];
+  if (m.kind == kRice) {
+    sink.put(m.hdr, 2);
+    const uint32_t k = m.k, marker = 1u << k, mask = marker - 1u;
+    for (uint32_t i = 0; i < len; i++) {
+      int32_t x = s[start + i];
+      uint32_t u = fold(x - prev);
+      prev = x;
+      uint32_t q = u >> k;
+      while (q >= 32u) {  // only reachable with thresholds far beyond the reference's table domains
+        sink.put(0u, 32u);
+        sink.flush();
+        q -= 32u;
+      }
+      sink.put(0u, q);
+      sink.flush();
+      sink.put(marker | (u & mask), k + 1u);
+      sink.flush();
+    }
+  } else if (m.kind == kBfp) {
+    sink.put(m.hdr, 6);
+    const uint32_t w = m.k + 1u, mask = (1u << w) - 1u;
+    for (uint32_t i = 0; i < len; i++) {
+      int32_t x = s[start + i];
+      sink.put((uint32_t)(x - prev) & mask, w);
+      sink.flush();
+      prev = x;
+    }
+  } else {
+    sink.put(15u, 6);
+    for (uint32_t i = 0; i < len; i++) {
+      sink.put((uint32_t)(uint16_t)s[start + i], 16);
+      sink.flush();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fast path: Parameters::default() (block_len 20, codes 0/1/3, thresholds 3/8/20) and a block of
+// 19 or 20 samples.  One pass over shared memory; the folded differences stay in registers.
+// ---------------------------------------------------------------------------------------------
+constexpr int kFastBL = 20;
+
+struct FastBlock {
+  uint32_t u[kFastBL];  // folded first differences
+  int32_t pred;         // sample before the block
+};
+
+X3_HD bool params_are_default(const CodecParams &P) {
+  return P.block_len == 20 && P.codes[0] == 0 && P.codes[1] == 1 && P.codes[2] == 3 && P.thresholds[0] == 3 &&
+         P.thresholds[1] == 8 && P.thresholds[2] == 20;
+}
+
+// reads s[start-1 .. start+19]; sample 19 is ignored (u=0) when len == 19
+X3_HD BlockMode block_measure_fast(const int16_t *s, uint32_t start, uint32_t len, FastBlock &fb, uint32_t &nbits) {
+  int32_t prev = s[start - 1];
+  fb.pred = prev;
+  uint32_t maxu = 0, sumu = 0;
+#pragma unroll
+  for (int i = 0; i < kFastBL; i++) {
+    int32_t x = s[start + i];
+    uint32_t u = fold(x - prev);
+    if (i == kFastBL - 1 && len != (uint32_t)kFastBL) u = 0;
+    prev = x;
+    fb.u[i] = u;
+    maxu = u > maxu ? u : maxu;
+    sumu += u;
+  }
+  const uint32_t max_abs = (maxu + 1u) >> 1;
+  BlockMode m;
+  uint32_t sum_q = sumu;
+  if (max_abs <= 20u) {
+    uint32_t ftype = (max_abs > 3u) + (max_abs > 8u);
+    m.kind = kRice;
+    m.k = ftype == 0 ? 0u : (ftype == 1 ? 1u : 3u);
+    m.hdr = ftype + 1;
+    m.stat = m.k;
+    if (m.k) {
+      sum_q = 0;
+#pragma unroll
+      for (int i = 0; i < kFastBL; i++) sum_q += fb.u[i] >> m.k;
+    }
+  } else {
+    uint32_t nb = 32u - clz32(max_abs);
+    if (nb >= 15) { m.kind = kLiteral; m.k = 15; m.hdr = 15; m.stat = 5; }
+    else { m.kind = kBfp; m.k = nb; m.hdr = nb; m.stat = 4; }
+  }
+  nbits = block_bits(m, len, sum_q);
+  return m;
+}
+
+X3_HD void block_pack_fast(const FastBlock &fb, uint32_t len, const BlockMode &m, BitSink &sink) {
+  if (m.kind == kRice) {
+    // codeword = (u>>k) zeros, then 1, then the k low bits of u; at the default thresholds it is at most
+    // 10 bits (RICE1, u<=16), so three codewords fit between flushes (31 + 30 <= 64).
+    sink.put(m.hdr, 2);
+    const uint32_t k = m.k, marker = 1u << k, mask = marker - 1u, k1 = k + 1u;
+#pragma unroll
+    for (int i = 0; i < kFastBL; i++) {
+      if (i < kFastBL - 1 || len == (uint32_t)kFastBL) {
+        uint32_t u = fb.u[i];
+        sink.put(marker | (u & mask), (u >> k) + k1);
+      }
+      if (i % 3 == 2 || i == kFastBL - 1) sink.flush();
+    }
+  } else if (m.kind == kBfp) {
+    sink.put(m.hdr, 6);
+    sink.flush();  // 31 + 6 + 2*15 would overflow the 64-bit accumulator
+    const uint32_t w = m.k + 1u, mask = (1u << w) - 1u;  // w <= 15
+#pragma unroll
+    for (int i = 0; i < kFastBL; i++) {
+      if (i < kFastBL - 1 || len == (uint32_t)kFastBL) sink.put((uint32_t)unfold(fb.u[i]) & mask, w);
+      if (i % 2 == 1) sink.flush();
+    }
+  } else {
+    sink.put(15u, 6);
+    sink.flush();
+    int32_t x = fb.pred;
+#pragma unroll
+    for (int i = 0; i < kFastBL; i++) {
+      if (i < kFastBL - 1 || len == (uint32_t)kFastBL) {
+        x += unfold(fb.u[i]);
+        sink.put((uint32_t)x & 0xffffu, 16);
+      }
+      if (i % 2 == 1) sink.flush();
+    }
+  }
+}
+
+// payload bytes for a payload of total_bits bits: pad to a byte, then to an even length
+// (BitPacker::word_align, bitpacker.rs:124-132; the payload starts at an even stream position)
+X3_HD uint32_t payload_bytes(uint32_t total_bits) { return ((total_bits + 15u) >> 4) << 1; }
+
+}  // namespace x3

@@ -1,0 +1,335 @@
+// x3_encode.cu -- frame encoder kernel for sm_100a.
+//
+// One CTA encodes one frame at a time (persistent CTAs, frames handed out by an atomic ticket):
+//   1. the frame's PCM is staged in shared memory with 16-byte cp.async copies;
+//   2. one thread per block: first difference, zig-zag fold, max -> mode (encoder.rs:304-314), bit length;
+//   3. CTA-wide exclusive scan of the bit lengths -> bit offset of every block inside the frame;
+//   4. each thread packs its block MSB-first straight into its final position in a shared-memory byte
+//      image (x3_enc_core.cuh: one writer per word, no atomics);
+//   5. CRC-16 of the payload: 16-byte chunks in parallel, combined by one warp (Horner + shuffle tree with
+//      multiply-by-x^n tables), header built (encoder.rs:122-162);
+//   6. decoupled look-back over the frame sizes gives the frame's byte offset in the output stream;
+//   7. the image is copied to global memory with coalesced stores.
+// HBM traffic is exactly the algorithmic figure: every PCM byte read once, every output byte written once
+// (plus 8 bytes of look-back status per frame).
+#include <cuda_runtime.h>
+
+#include "x3_enc_core.cuh"
+#include "x3_kernels.h"
+#include "x3_lookback.cuh"
+
+namespace x3 {
+
+namespace {
+
+constexpr int NT = kEncThreads;
+constexpr int NW = NT / 32;
+
+// stage frame f's samples into shared memory (asynchronously where 16-byte alignment allows)
+__device__ __forceinline__ void issue_frame_load(const EncodeArgs &a, uint32_t f, int16_t *s_in) {
+  const unsigned long long s0 = (unsigned long long)f * a.P.spf;
+  unsigned long long rem = a.n_samples - s0;
+  const uint32_t n = rem < a.P.spf ? (uint32_t)rem : a.P.spf;
+  const int16_t *src = a.pcm + s0;
+  uint32_t done = 0;
+  if ((((uintptr_t)src) & 15u) == 0) {
+    const uint32_t chunks = n >> 3;  // 8 samples = 16 bytes
+    for (uint32_t c = threadIdx.x; c < chunks; c += NT) cp_async16(s_in + c * 8, src + c * 8);
+    done = chunks << 3;
+  }
+  for (uint32_t i = done + threadIdx.x; i < n; i += NT) s_in[i] = __ldg(src + i);
+  cp_async_commit();
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(NT, FAST ? 2 : 1) encode_frames_kernel(const EncodeArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // ---- shared memory carve-up (all offsets 16-byte aligned) ----
+  const uint32_t in_bytes = (2u * (a.P.spf + 8u) + 15u) & ~15u;
+  const uint32_t img_bytes = 32u + 4u * (a.out_words_cap + 8u);
+  const uint32_t nblk_cap = a.max_blocks + 2u;
+  unsigned char *p = smem_raw;
+  int16_t *s_in = reinterpret_cast<int16_t *>(p);                 p += in_bytes;
+  unsigned char *s_img = p;                                        p += (img_bytes + 15u) & ~15u;
+  uint16_t *s_crcT = reinterpret_cast<uint16_t *>(p);             p += kCrcTableEntries * 2;
+  uint32_t *s_offs = reinterpret_cast<uint32_t *>(p);             p += ((nblk_cap * 4u) + 15u) & ~15u;
+  uint32_t *s_Hs = reinterpret_cast<uint32_t *>(p);               p += ((nblk_cap * 4u) + 15u) & ~15u;
+  uint32_t *s_Ts = reinterpret_cast<uint32_t *>(p);               p += ((nblk_cap * 4u) + 15u) & ~15u;
+  uint16_t *s_chunk = reinterpret_cast<uint16_t *>(p);            p += (((a.out_words_cap / 4u + 2u) * 2u) + 15u) & ~15u;
+  uint32_t *s_misc = reinterpret_cast<uint32_t *>(p);
+  // s_misc: [0..NW) warp totals, [32] next ticket, [33] payload crc, [34..36) out offset (u64), [40..46) stats adj
+  uint32_t *s_words = reinterpret_cast<uint32_t *>(s_img + 32);   // payload words
+  uint32_t *s_hdr = reinterpret_cast<uint32_t *>(s_img + 12);     // 5 header words
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint32_t BL = a.P.block_len;
+
+  for (int i = tid; i < kCrcTableEntries; i += NT) s_crcT[i] = a.crc_tables[i];
+  if (tid < 6) s_misc[40 + tid] = 0;
+  if (tid == 0) s_misc[32] = atomicAdd(a.ticket, 1u);
+  __syncthreads();
+  uint32_t f = s_misc[32];
+  if (f < a.n_frames) issue_frame_load(a, f, s_in);
+
+  uint32_t full_block_count = 0;  // lane m < 6 of every warp counts full blocks coded in mode m
+
+  while (f < a.n_frames) {
+    const unsigned long long s0 = (unsigned long long)f * a.P.spf;
+    const unsigned long long remn = a.n_samples - s0;
+    const uint32_t n = remn < a.P.spf ? (uint32_t)remn : a.P.spf;
+    const uint32_t nblk = n > 1 ? (n - 2u) / BL + 1u : 1u;  // ceil((n-1)/BL), at least one (possibly empty) block
+    const uint32_t rounds = (nblk + NT - 1) / NT;
+
+    cp_async_wait_all();
+    __syncthreads();  // (A) input staged; previous frame's image fully copied out
+
+    uint32_t bit_base = 0;
+    uint32_t f_next = a.n_frames;
+    for (uint32_t r = 0; r < rounds; r++) {
+      const uint32_t b = r * NT + tid;
+      const bool active = b < nblk;
+      const uint32_t start = 1u + b * BL;
+      uint32_t len = 0;
+      if (active && n > start) len = (n - start) < BL ? (n - start) : BL;
+
+      // ---- measure ----
+      FastBlock fb;
+      BlockMode mode;
+      mode.kind = kRice; mode.k = 0; mode.hdr = 0; mode.stat = 0;
+      uint32_t nbits = 0;
+      bool use_fast = false;
+      if (active) {
+        if (FAST && len >= (uint32_t)kFastBL - 1) {
+          use_fast = true;
+          mode = block_measure_fast(s_in, start, len, fb, nbits);
+        } else if (len > 0) {
+          mode = block_measure_generic(s_in, start, len, a.P, nbits);
+        }
+        if (b == 0) nbits += 16;  // <Audio State>: first sample as 16 raw bits, encoder.rs:189
+      }
+
+      // ---- statistics (stats[ftype] += block.len(), encoder.rs:199) ----
+      {
+        const bool full = active && len == BL;
+#pragma unroll
+        for (int m = 0; m < 6; m++) {
+          unsigned bal = __ballot_sync(0xffffffffu, full && mode.stat == (uint32_t)m);
+          if (lane == m) full_block_count += __popc(bal);
+        }
+        if (active && len != BL && len > 0) atomicAdd(&s_misc[40 + mode.stat], len);
+      }
+
+      // ---- exclusive scan of nbits over the CTA ----
+      uint32_t incl = nbits;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      if (lane == 31) s_misc[wid] = incl;
+      if (tid == 0 && r == rounds - 1) s_misc[32] = atomicAdd(a.ticket, 1u);  // next frame for this CTA
+      __syncthreads();  // (B) warp totals visible; every thread has finished reading s_in for this round
+      uint32_t wt = lane < NW ? s_misc[lane] : 0u;
+      uint32_t wincl = wt;
+#pragma unroll
+      for (int d = 1; d < NW; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, wincl, d);
+        if (lane >= d) wincl += t;
+      }
+      const uint32_t round_total = __shfl_sync(0xffffffffu, wincl, NW - 1);
+      const uint32_t warp_base = __shfl_sync(0xffffffffu, wincl - wt, wid);
+      const uint32_t bit_off = bit_base + warp_base + (incl - nbits);
+      bit_base += round_total;
+      if (active) s_offs[b] = bit_off;
+
+      if (FAST && r == rounds - 1) {
+        // All reads of s_in by the fast path are done (the folded differences live in registers), so the
+        // next frame can stream in while this one is packed.  Blocks on the generic path re-read s_in, but
+        // they only occur in the stream's final frame, after which there is nothing to prefetch.
+        f_next = s_misc[32];
+        if (f_next < a.n_frames) issue_frame_load(a, f_next, s_in);
+      }
+
+      // ---- pack ----
+      if (active) {
+        BitSink sink;
+        sink.init(bit_off, s_words, &s_Hs[b]);
+        if (b == 0) {
+          sink.put((uint32_t)(uint16_t)(use_fast ? fb.pred : (int32_t)s_in[0]), 16);
+          sink.flush();
+        }
+        if (use_fast) block_pack_fast(fb, len, mode, sink);
+        else if (len > 0) block_pack_generic(s_in, start, len, mode, sink);
+        bool has_tail;
+        uint32_t timg = sink.finish(has_tail);
+        s_Ts[b] = timg;
+      }
+      if (r + 1 < rounds) __syncthreads();  // (C) s_misc warp totals are rewritten by the next round
+    }
+    const uint32_t total_bits = bit_base;
+    const uint32_t payload_len = payload_bytes(total_bits);
+    const uint32_t frame_bytes = (uint32_t)kFrameHeaderLen + payload_len;
+    if (!FAST) f_next = s_misc[32];
+
+    if (tid == 0) {
+      s_offs[nblk] = total_bits;
+      s_offs[nblk + 1] = 0xffffffffu;
+      s_Hs[nblk] = 0u;
+      s_Hs[nblk + 1] = 0u;
+      // publish this frame's size so later frames can look back over it
+      st_status(a.status + f, (f == 0 ? kFlagPrefix : kFlagAgg) | (unsigned long long)frame_bytes);
+    }
+    __syncthreads();  // (D) heads, tails, offsets visible
+
+    // ---- merge: the owner of every partially filled word ORs in the heads that follow it ----
+    for (uint32_t b = tid; b < nblk; b += NT) {
+      const uint32_t end = s_offs[b + 1];
+      if (end & 31u) {
+        const uint32_t lw = end >> 5;
+        const uint32_t o = s_offs[b];
+        if ((o >> 5) < lw || (o & 31u) == 0u) {
+          uint32_t v = s_Ts[b] | s_Hs[b + 1];
+          for (uint32_t j = b + 2; (s_offs[j] >> 5) == lw; j++) v |= s_Hs[j];  // short blocks: several heads per word
+          s_words[lw] = v;
+        }
+      }
+    }
+    __syncthreads();  // (E) payload image complete
+
+    // ---- payload CRC, phase A: 16-byte chunks, each from a zero state (chunk 0 from 0xffff) ----
+    const uint32_t m_full = payload_len >> 4;
+    for (uint32_t c = tid; c < m_full; c += NT) {
+      const uint4 q = reinterpret_cast<const uint4 *>(s_words)[c];
+      uint32_t s = c == 0 ? 0xffffu : 0u;
+      s = crc16_word(s_crcT, s, bswap32(q.x));
+      s = crc16_word(s_crcT, s, bswap32(q.y));
+      s = crc16_word(s_crcT, s, bswap32(q.z));
+      s = crc16_word(s_crcT, s, bswap32(q.w));
+      s_chunk[c] = (uint16_t)s;
+    }
+    __syncthreads();  // (F)
+
+    if (wid == 0) {
+      // ---- phase B: combine.  With e = m_full-1-c the distance of chunk c from the end, the state after
+      // all full chunks is  sum_e chunk[e] * x^(128 e).  Lane l takes e = l, l+32, ... (Horner in x^4096),
+      // then a shuffle tree multiplies by x^(128*2^k). ----
+      uint32_t h = 0;
+      if (m_full > (uint32_t)lane) {
+        for (int i = (int)((m_full - 1u - lane) >> 5); i >= 0; i--) {
+          const uint32_t c = m_full - 1u - (32u * (uint32_t)i + lane);
+          h = crc16_mulc(s_crcT, 4, h) ^ (uint32_t)s_chunk[c];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 5; k++) {
+        uint32_t o = __shfl_down_sync(0xffffffffu, h, 1 << k);
+        h ^= crc16_mulc(s_crcT, 6 + 2 * k, o);
+      }
+      if (lane == 0) {
+        uint32_t s = m_full ? h : 0xffffu;
+        const uint32_t rem = payload_len & 15u;  // even
+        uint32_t wi = m_full * 4u;
+        for (uint32_t done = 0; done + 4u <= rem; done += 4u) s = crc16_word(s_crcT, s, bswap32(s_words[wi++]));
+        if (rem & 2u) s = crc16_half(s_crcT, s, bswap32(s_words[wi]) >> 16);
+        // ---- frame header, encoder.rs:122-162 (id = 1 for audio frames, encoder.rs:210) ----
+        const uint32_t hc = header_crc(s_crcT, 1u, n, payload_len);
+        s_hdr[0] = bswap32((kFrameKey << 16) | 0x0101u);
+        s_hdr[1] = bswap32(((n & 0xffffu) << 16) | (payload_len & 0xffffu));
+        s_hdr[2] = 0u;
+        s_hdr[3] = 0u;
+        s_hdr[4] = bswap32((hc << 16) | (s & 0xffffu));
+      }
+    } else if (wid == 1) {
+      // ---- decoupled look-back over frame sizes -> this frame's byte offset ----
+      const unsigned long long excl = lookback_exclusive(a.status, f, frame_bytes);
+      if (lane == 0) {
+        s_misc[34] = (uint32_t)excl;
+        s_misc[35] = (uint32_t)(excl >> 32);
+        if (f == a.n_frames - 1) a.result[0] = excl + frame_bytes;  // total stream length
+      }
+    }
+    __syncthreads();  // (G) header + offset ready
+
+    // ---- copy the frame image to its place in the output stream ----
+    {
+      const unsigned long long off = (unsigned long long)s_misc[34] | ((unsigned long long)s_misc[35] << 32);
+      if (off + frame_bytes <= a.out_cap) {
+        unsigned char *dst = a.out + off;
+        const uint32_t *src32 = s_hdr;
+        const uint32_t L = frame_bytes;
+        const uintptr_t al = (uintptr_t)dst & 3u;
+        if (al == 0) {
+          uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
+          const uint32_t nw = L >> 2;
+          for (uint32_t i = tid; i < nw; i += NT) d32[i] = src32[i];
+          if ((L & 2u) && tid == 0)
+            *reinterpret_cast<uint16_t *>(dst + (nw << 2)) = (uint16_t)(src32[nw] & 0xffffu);
+        } else if (al == 2) {
+          if (tid == 0) *reinterpret_cast<uint16_t *>(dst) = (uint16_t)(src32[0] & 0xffffu);
+          uint32_t *d32 = reinterpret_cast<uint32_t *>(dst + 2);
+          const uint32_t nw = (L - 2u) >> 2;
+          for (uint32_t i = tid; i < nw; i += NT) d32[i] = __byte_perm(src32[i], src32[i + 1], 0x5432);
+          if (((L - 2u) & 2u) && tid == 0)
+            *reinterpret_cast<uint16_t *>(dst + 2 + (nw << 2)) = (uint16_t)(src32[nw] >> 16);
+        } else {
+          const unsigned char *sb = reinterpret_cast<const unsigned char *>(s_hdr);
+          for (uint32_t i = tid; i < L; i += NT) dst[i] = sb[i];
+        }
+      } else if (tid == 0) {
+        atomicMax(a.result + 1, 1ull);  // ByteWriterInsufficientMemory, bytewriter.rs:88-90
+      }
+    }
+
+    f = f_next;
+    if (!FAST && f < a.n_frames) {
+      __syncthreads();  // generic path re-reads s_in while packing, so only now may it be overwritten
+      issue_frame_load(a, f, s_in);
+    }
+  }
+
+  // ---- flush statistics ----
+  if (lane < 6 && full_block_count) atomicAdd(a.result + 2 + lane, (unsigned long long)full_block_count * BL);
+  __syncthreads();
+  if (tid < 6 && s_misc[40 + tid]) atomicAdd(a.result + 2 + tid, (unsigned long long)s_misc[40 + tid]);
+}
+
+}  // namespace
+
+size_t encode_smem_bytes(const CodecParams &P, uint32_t max_blocks, uint32_t out_words_cap) {
+  const uint32_t in_bytes = (2u * (P.spf + 8u) + 15u) & ~15u;
+  const uint32_t img_bytes = (32u + 4u * (out_words_cap + 8u) + 15u) & ~15u;
+  const uint32_t nblk_cap = max_blocks + 2u;
+  const uint32_t arr = ((nblk_cap * 4u) + 15u) & ~15u;
+  const uint32_t chunk = (((out_words_cap / 4u + 2u) * 2u) + 15u) & ~15u;
+  return (size_t)in_bytes + img_bytes + kCrcTableEntries * 2 + 3u * arr + chunk + 64u * 4u;
+}
+
+cudaError_t launch_encode(const EncodeArgs &a, bool fast, int grid, size_t smem, cudaStream_t stream) {
+  cudaError_t e;
+  if (fast) {
+    e = cudaFuncSetAttribute(encode_frames_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    encode_frames_kernel<true><<<grid, NT, smem, stream>>>(a);
+  } else {
+    e = cudaFuncSetAttribute(encode_frames_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    encode_frames_kernel<false><<<grid, NT, smem, stream>>>(a);
+  }
+  return cudaGetLastError();
+}
+
+int encode_occupancy(bool fast, size_t smem) {
+  int nb = 0;
+  cudaError_t e;
+  if (fast) {
+    cudaFuncSetAttribute(encode_frames_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, encode_frames_kernel<true>, NT, smem);
+  } else {
+    cudaFuncSetAttribute(encode_frames_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, encode_frames_kernel<false>, NT, smem);
+  }
+  if (e != cudaSuccess || nb < 1) nb = 1;
+  return nb;
+}
+
+}  // namespace x3

@@ -1,0 +1,80 @@
+// x3_kernels.h -- host-visible launch interface of the CUDA kernels (internal to libx3b200.so).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "x3_common.cuh"
+
+namespace x3 {
+
+constexpr int kEncThreads = 512;
+constexpr int kDecThreads = 128;
+constexpr int kScanThreads = 256;
+
+struct EncodeArgs {
+  const int16_t *pcm;
+  unsigned long long n_samples;
+  uint8_t *out;
+  unsigned long long out_cap;
+  CodecParams P;
+  uint32_t n_frames;
+  uint32_t max_blocks;      // blocks in a full frame
+  uint32_t out_words_cap;   // 32-bit words of payload image a frame can need
+  unsigned long long *status;  // [n_frames] look-back words, zeroed before launch
+  unsigned int *ticket;        // zeroed before launch
+  unsigned long long *result;  // [0] total bytes, [1] overflow flag, [2..8) stats; zeroed before launch
+  const uint16_t *crc_tables;  // kCrcTableEntries
+};
+
+size_t encode_smem_bytes(const CodecParams &P, uint32_t max_blocks, uint32_t out_words_cap);
+int encode_occupancy(bool fast, size_t smem);
+cudaError_t launch_encode(const EncodeArgs &a, bool fast, int grid, size_t smem, cudaStream_t stream);
+
+// One frame of a stream, as found by the frame index (device scan or host walk).
+struct FrameRec {
+  unsigned long long pos;      // byte offset of the frame header in the stream
+  unsigned long long out_off;  // sample offset of the frame's first sample in the PCM output
+  uint32_t samples;            // header.samples
+  uint32_t payload_len;        // header.payload_len
+  uint32_t payload_crc;        // header.payload_crc
+  uint32_t pad;
+};
+
+struct DecodeArgs {
+  const uint8_t *stream;
+  unsigned long long stream_len;
+  int16_t *pcm;
+  unsigned long long pcm_cap;
+  CodecParams P;
+  const FrameRec *frames;
+  const unsigned long long *n_frames;  // device scalar (the index kernel produces it)
+  unsigned long long max_frames;       // capacity of `frames` / status
+  int *frame_status;                   // [max_frames]
+  unsigned long long *result;          // [0] first bad frame (init ~0), [1] unused
+  const uint16_t *crc_tables;
+};
+
+cudaError_t launch_crc(const DecodeArgs &a, unsigned long long n_frames_hint, cudaStream_t stream);
+cudaError_t launch_decode(const DecodeArgs &a, unsigned long long n_frames_hint, cudaStream_t stream);
+
+struct ScanArgs {
+  const uint8_t *stream;
+  unsigned long long stream_len;
+  FrameRec *frames;
+  unsigned long long max_frames;
+  unsigned long long *tile_status;  // [n_tiles] look-back words, zeroed
+  unsigned int *ticket;             // zeroed
+  unsigned long long *result;       // [0] n_frames, [1] total samples, [2] flags (1 = needs host walk)
+  const uint16_t *crc_tables;
+  uint32_t n_tiles;
+};
+constexpr uint32_t kScanTileBytes = 64 * 1024;
+cudaError_t launch_scan(const ScanArgs &a, cudaStream_t stream);
+cudaError_t launch_chain_check(const ScanArgs &a, cudaStream_t stream);
+
+cudaError_t launch_synth(int kind, uint32_t seed, uint32_t fs, unsigned long long n0, unsigned long long count,
+                         int16_t *out, cudaStream_t stream);
+
+}  // namespace x3

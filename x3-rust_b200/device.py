@@ -1,0 +1,70 @@
+"""Device-resident entry points: torch CUDA tensors in, torch CUDA tensors out (zero-copy over the C ABI).
+
+PyTorch is plumbing only here: it owns the device memory and the stream; all compute is libx3b200.so.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib, error, x3
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def encode_tensor(pcm, params=None, out=None):
+    """int16 CUDA tensor -> (uint8 CUDA tensor holding the frame stream, length, stats[6])."""
+    params = params or x3.Parameters.default()
+    assert pcm.is_cuda and pcm.dtype == torch.int16 and pcm.is_contiguous()
+    L = _lib.lib()
+    ps = params.c_struct()
+    n = pcm.numel()
+    with torch.cuda.device(pcm.device):
+        if out is None:
+            out = torch.empty(max(int(L.x3_encode_bound(n, C.byref(ps))), 1), dtype=torch.uint8, device=pcm.device)
+        out_len = C.c_size_t()
+        st = _lib.x3_stats()
+        error.check(L.x3_encode_device(C.c_void_p(pcm.data_ptr()), n, C.byref(ps), C.c_void_p(out.data_ptr()),
+                                       out.numel(), C.byref(out_len), C.byref(st), _stream_ptr()))
+    return out, out_len.value, [int(v) for v in st.samples_by_mode]
+
+
+def decode_tensor(frames, length, params=None, out=None, max_samples=None):
+    """uint8 CUDA tensor with a frame stream of `length` bytes -> (int16 CUDA tensor, n_samples, result, code)."""
+    params = params or x3.Parameters.default()
+    assert frames.is_cuda and frames.dtype == torch.uint8 and frames.is_contiguous()
+    L = _lib.lib()
+    ps = params.c_struct()
+    with torch.cuda.device(frames.device):
+        if out is None:
+            assert max_samples is not None
+            out = torch.empty(max(max_samples, 1), dtype=torch.int16, device=frames.device)
+        n = C.c_size_t()
+        r = _lib.x3_decode_result()
+        code = L.x3_decode_device(C.c_void_p(frames.data_ptr()), length, C.byref(ps), C.c_void_p(out.data_ptr()),
+                                  out.numel(), C.byref(n), C.byref(r), _stream_ptr())
+    if code in (error.CUDA, error.INVALID_ARGUMENT):
+        error.check(code)
+    from .decoder import DecodeResult
+    return out, n.value, DecodeResult(code, r), code
+
+
+def synth(kind, seed, fs, n0, count, device="cuda", out=None):
+    """Synthetic signal S1/S2/S4 generated on the device."""
+    L = _lib.lib()
+    if out is None:
+        out = torch.empty(count, dtype=torch.int16, device=device)
+    with torch.cuda.device(out.device):
+        error.check(L.x3_synth_device(kind, seed, fs, n0, count, C.c_void_p(out.data_ptr()), _stream_ptr()))
+    return out
+
+
+def kernel_launch_count():
+    return int(_lib.lib().x3_kernel_launch_count())
+
+
+def last_kernel_ms():
+    ms = (C.c_float * 4)()
+    _lib.lib().x3_last_kernel_ms(C.byref(ms))
+    return [float(v) for v in ms]

@@ -113,7 +113,7 @@ def test_encode_matches_oracle_other_params(pkg, oracle):
     cases = [dict(bpf=10), dict(bpf=1), dict(block_len=1, bpf=7), dict(block_len=7, bpf=33),
              dict(block_len=60, bpf=100), dict(block_len=33, bpf=700), dict(codes=(0, 1, 2)),
              dict(codes=(1, 2, 3), th=(5, 11, 20)), dict(codes=(0, 0, 0), th=(1, 2, 6)),
-             dict(block_len=16, bpf=64, codes=(3, 1, 0), th=(3, 8, 6)), dict(th=(8, 3, 20)), dict(th=(3, 8, 2)),
+             dict(block_len=16, bpf=64, codes=(3, 1, 0), th=(3, 8, 6)), dict(th=(5, 3, 20)), dict(th=(3, 8, 2)),
              dict(bpf=1200), dict(block_len=5, bpf=3000)]
     for kw in cases:
         p, po = mk_params(pkg, oracle, **kw)

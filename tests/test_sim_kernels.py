@@ -91,7 +91,7 @@ def test_sim_encode_other_params(sim, oracle):
     sig = signals(oracle)
     cases = [P8(20, 10), P8(20, 1), P8(1, 7), P8(7, 33), P8(60, 100), P8(33, 700), P8(20, 500, (0, 1, 2)),
              P8(20, 500, (1, 2, 3), (5, 11, 20)), P8(20, 500, (0, 0, 0), (1, 2, 6)), P8(16, 64, (3, 1, 0), (3, 8, 6)),
-             P8(20, 500, (0, 1, 3), (8, 3, 20)), P8(20, 500, (0, 1, 3), (3, 8, 2)), P8(20, 1200), P8(5, 3000)]
+             P8(20, 500, (0, 1, 3), (5, 3, 20)), P8(20, 500, (0, 1, 3), (3, 8, 2)), P8(20, 1200), P8(5, 3000)]
     for p8 in cases:
         for name in ("s1", "s2b", "s4", "white", "small"):
             pcm = sig[name][:30000]

@@ -523,6 +523,7 @@ int x3_decode_device(const uint8_t *d_frames, size_t len, const x3_params *p, in
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return fail(e, "host walk copy");
     std::vector<FrameRec> frames;
+    total_samples = 0;
     walk_rc = host_walk(host.data(), len, frames, &total_samples);
     n_frames = frames.size();
     if (n_frames > max_frames) {

@@ -57,7 +57,94 @@ uint32_t crc_chunked(const uint32_t *words_img, uint32_t payload_len) {
   return s & 0xffffu;
 }
 
-// one frame, mirroring encode_frames_kernel<FAST> (single CTA, NT simulated threads)
+// CRC as the fast encode kernel does it: per-warp slices of 32 chunks (shuffle tree), then Horner over slices
+uint32_t crc_sliced(const uint32_t *words_img, uint32_t payload_len) {
+  const uint16_t *t = T();
+  const uint32_t m = payload_len >> 4, nslices = (m + 31u) >> 5;
+  std::vector<uint32_t> V(nslices + 1);
+  for (uint32_t j = 0; j < nslices; j++) {
+    uint32_t h[32];
+    for (uint32_t lane = 0; lane < 32; lane++) {
+      const uint32_t e = 32u * j + lane;
+      h[lane] = 0;
+      if (e < m) {
+        const uint32_t c = m - 1u - e;
+        uint32_t s = c == 0 ? 0xffffu : 0u;
+        for (int w = 0; w < 4; w++) s = crc16_word(t, s, bswap32(words_img[4 * c + w]));
+        h[lane] = s;
+      }
+    }
+    for (int k = 0; k < 5; k++) {
+      uint32_t o[32];
+      for (int lane = 0; lane < 32; lane++) o[lane] = lane + (1 << k) < 32 ? h[lane + (1 << k)] : h[lane];
+      for (int lane = 0; lane < 32; lane++) h[lane] ^= crc16_mulc(t, 6 + 2 * k, o[lane]);
+    }
+    V[j] = h[0];
+  }
+  uint32_t s = 0;
+  for (int j = (int)nslices - 1; j >= 0; j--) s = crc16_mulc(t, 4, s) ^ V[j];
+  if (m == 0) s = 0xffffu;
+  const uint32_t rem = payload_len & 15u;
+  uint32_t wi = m * 4u;
+  for (uint32_t done = 0; done + 4u <= rem; done += 4u) s = crc16_word(t, s, bswap32(words_img[wi++]));
+  if (rem & 2u) s = crc16_half(t, s, bswap32(words_img[wi]) >> 16);
+  return s & 0xffffu;
+}
+
+// one frame, mirroring encode_frames_fast_kernel (16 worker warps; FastSink, one atomicOr per unaligned block)
+size_t sim_encode_frame_fast(const int16_t *pcm, uint32_t n, const CodecParams &P, bool last_frame, uint8_t *out,
+                             uint64_t stats[6]) {
+  const uint32_t BL = 20;
+  const uint32_t nblk = n > 1 ? (n - 2u) / BL + 1u : 1u;
+  std::vector<int16_t> s_in(n + 64, (int16_t)0x5a5a);
+  memcpy(s_in.data(), pcm, n * sizeof(int16_t));
+  std::vector<uint32_t> words((16u + nblk * 330u) / 32u + 16u, 0xdeadbeefu);
+  struct Th { bool active, use_fast; uint32_t len, nbits, start, bit_off; FastBlock fb; BlockMode mode; };
+  std::vector<Th> th(512);
+  std::vector<uint32_t> s_first(512, 0xdeadbeefu);
+  uint32_t run = 0;
+  for (int tid = 0; tid < 512; tid++) {
+    Th &t = th[tid];
+    const uint32_t b = tid;
+    t.active = b < nblk;
+    t.start = 1u + b * BL;
+    t.len = 0;
+    if (t.active && n > t.start) t.len = (n - t.start) < BL ? (n - t.start) : BL;
+    t.mode.kind = kRice; t.mode.k = 0; t.mode.hdr = 0; t.mode.stat = 0;
+    t.nbits = 0; t.use_fast = false;
+    if (t.active) {
+      if (t.len >= BL - 1) { t.use_fast = true; t.mode = block_measure_fast(s_in.data(), t.start, t.len, t.fb, t.nbits); }
+      else if (t.len > 0) t.mode = block_measure_generic(s_in.data(), t.start, t.len, P, t.nbits);
+      if (b == 0) t.nbits += 16;
+      if (t.len > 0) stats[t.mode.stat] += t.len;
+    }
+    t.bit_off = run;
+    run += t.nbits;
+  }
+  const uint32_t total_bits = run, payload_len = payload_bytes(total_bits);
+  std::vector<int16_t> s_in_pack = s_in;
+  if (!last_frame) std::fill(s_in_pack.begin(), s_in_pack.end(), (int16_t)0x7b7b);  // next frame's prefetch
+  for (int tid = 0; tid < 512; tid++) {
+    Th &t = th[tid];
+    if (!t.active) continue;
+    FastSink sink;
+    sink.init(t.bit_off, words.data(), &s_first[tid]);
+    if (tid == 0) { sink.put((uint32_t)(uint16_t)(t.use_fast ? t.fb.pred : (int32_t)s_in_pack[0]), 16); sink.flush(); }
+    if (t.use_fast) block_pack_fast(t.fb, t.len, t.mode, sink);
+    else { if (t.len > 0) block_pack_generic(s_in_pack.data(), t.start, t.len, t.mode, sink); sink.finish(); }
+  }
+  for (int tid = 0; tid < 512; tid++)
+    if (th[tid].active && (th[tid].bit_off & 31u)) words[th[tid].bit_off >> 5] |= s_first[tid];  // atomicOr
+  const uint32_t crc = crc_sliced(words.data(), payload_len);
+  const uint32_t hc = header_crc(T(), 1u, n, payload_len);
+  uint32_t hdr[5] = {bswap32((kFrameKey << 16) | 0x0101u), bswap32(((n & 0xffffu) << 16) | (payload_len & 0xffffu)), 0u, 0u,
+                     bswap32((hc << 16) | crc)};
+  memcpy(out, hdr, 20);
+  memcpy(out + 20, words.data(), payload_len);
+  return 20 + payload_len;
+}
+
+// one frame, mirroring encode_frames_generic_kernel (single CTA, NT simulated threads)
 size_t sim_encode_frame(const int16_t *pcm, uint32_t n, const CodecParams &P, bool fast_kernel, bool last_frame,
                         uint8_t *out, uint64_t stats[6]) {
   const uint32_t BL = P.block_len;
@@ -83,10 +170,7 @@ size_t sim_encode_frame(const int16_t *pcm, uint32_t n, const CodecParams &P, bo
       t.nbits = 0;
       t.use_fast = false;
       if (t.active) {
-        if (fast_kernel && t.len >= (uint32_t)kFastBL - 1) {
-          t.use_fast = true;
-          t.mode = block_measure_fast(s_in.data(), t.start, t.len, t.fb, t.nbits);
-        } else if (t.len > 0) {
+        if (t.len > 0) {
           t.mode = block_measure_generic(s_in.data(), t.start, t.len, P, t.nbits);
         }
         if (b == 0) t.nbits += 16;
@@ -112,8 +196,7 @@ size_t sim_encode_frame(const int16_t *pcm, uint32_t n, const CodecParams &P, bo
         sink.put((uint32_t)(uint16_t)(t.use_fast ? t.fb.pred : (int32_t)s_in_pack[0]), 16);
         sink.flush();
       }
-      if (t.use_fast) block_pack_fast(t.fb, t.len, t.mode, sink);
-      else if (t.len > 0) block_pack_generic(s_in_pack.data(), t.start, t.len, t.mode, sink);
+      if (t.len > 0) block_pack_generic(s_in_pack.data(), t.start, t.len, t.mode, sink);
       bool has_tail;
       Ts[b] = sink.finish(has_tail);
     }
@@ -150,12 +233,13 @@ int sim_encode(const int16_t *pcm, size_t n, const uint32_t *params /*bl,bpf,c0,
   P.block_len = params[0];
   P.spf = params[0] * params[1];
   for (int k = 0; k < 3; k++) { P.codes[k] = params[2 + k]; P.thresholds[k] = params[5 + k]; }
-  const bool fast = params_are_default(P) && !force_generic;
+  const bool fast = params_are_default(P) && params[1] <= 512 && !force_generic;
   size_t pos = 0;
   for (size_t s0 = 0; s0 < n; s0 += P.spf) {
     const uint32_t fn = (uint32_t)((n - s0) < P.spf ? (n - s0) : P.spf);
     std::vector<uint8_t> tmp(64 + 2 * (size_t)fn * 9);
-    const size_t L = sim_encode_frame(pcm + s0, fn, P, fast, s0 + fn >= n, tmp.data(), stats);
+    const size_t L = fast ? sim_encode_frame_fast(pcm + s0, fn, P, s0 + fn >= n, tmp.data(), stats)
+                          : sim_encode_frame(pcm + s0, fn, P, false, s0 + fn >= n, tmp.data(), stats);
     if (pos + L > cap) return -15;
     memcpy(out + pos, tmp.data(), L);
     pos += L;

@@ -150,8 +150,8 @@ int derive(const x3_params *p, Derived *d) {
   d->max_block_bits = max_block_bits_of(p);
   const unsigned long long bits = 16ull + (unsigned long long)d->max_blocks * d->max_block_bits;
   d->out_words_cap = (uint32_t)((bits + 31ull) / 32ull) + 1u;
-  d->fast = params_are_default(d->P);
-  d->smem = encode_smem_bytes(d->P, d->max_blocks, d->out_words_cap);
+  d->fast = params_are_default(d->P) && d->max_blocks <= 512u;
+  d->smem = d->fast ? encode_fast_smem_bytes(d->P, d->out_words_cap) : encode_smem_bytes(d->P, d->max_blocks, d->out_words_cap);
   if (d->smem > kMaxDynSmem) return X3_ERR_UNSUPPORTED_PARAMS;
   return X3_OK;
 }

@@ -134,10 +134,12 @@ X3_HD BlockMode block_measure_generic(const int16_t *s, uint32_t start, uint32_t
   return m;
 }
 
-X3_HD void block_pack_generic(const int16_t *s, uint32_t start, uint32_t len, const BlockMode &m, BitSink &sink) {
+template <class Sink>
+X3_HD void block_pack_generic(const int16_t *s, uint32_t start, uint32_t len, const BlockMode &m, Sink &sink) {
   int32_t prev = s[start - 1];
   if (m.kind == kRice) {
     sink.put(m.hdr, 2);
+    sink.flush();
     const uint32_t k = m.k, marker = 1u << k, mask = marker - 1u;
     for (uint32_t i = 0; i < len; i++) {
       int32_t x = s[start + i];
@@ -156,6 +158,7 @@ X3_HD void block_pack_generic(const int16_t *s, uint32_t start, uint32_t len, co
     }
   } else if (m.kind == kBfp) {
     sink.put(m.hdr, 6);
+    sink.flush();
     const uint32_t w = m.k + 1u, mask = (1u << w) - 1u;
     for (uint32_t i = 0; i < len; i++) {
       int32_t x = s[start + i];
@@ -165,6 +168,7 @@ X3_HD void block_pack_generic(const int16_t *s, uint32_t start, uint32_t len, co
     }
   } else {
     sink.put(15u, 6);
+    sink.flush();
     for (uint32_t i = 0; i < len; i++) {
       sink.put((uint32_t)(uint16_t)s[start + i], 16);
       sink.flush();
@@ -226,42 +230,88 @@ X3_HD BlockMode block_measure_fast(const int16_t *s, uint32_t start, uint32_t le
   return m;
 }
 
-X3_HD void block_pack_fast(const FastBlock &fb, uint32_t len, const BlockMode &m, BitSink &sink) {
+// MSB-first bit sink of the fast kernel.  A block whose first bit is not word aligned keeps its first word
+// out of the image (it goes to `first_slot`) and ORs it into place with one shared-memory atomic after all
+// plain stores are done; every other word -- including the zero-padded last partial word -- is a plain store
+// to its final position.  (The predecessor's last word, stored plainly, is the base the head is ORed into.)
+struct FastSink {
+  uint64_t acc;
+  uint32_t cnt;
+  uint32_t *dst;
+  uint32_t *nxt;
+  X3_HD void init(uint32_t bit_off, uint32_t *out_words, uint32_t *first_slot) {
+    acc = 0;
+    cnt = bit_off & 31u;
+    uint32_t *w = out_words + (bit_off >> 5);
+    dst = cnt ? first_slot : w;
+    nxt = w + 1;
+  }
+  X3_HD void put(uint32_t v, uint32_t n) {  // v < 2^n, n <= 32, cnt + n <= 64
+    acc = (acc << n) | (uint64_t)v;
+    cnt += n;
+  }
+  X3_HD void flush() {
+    if (cnt >= 32u) {
+      cnt -= 32u;
+      *dst = bswap32((uint32_t)(acc >> cnt));
+      dst = nxt;
+      nxt = nxt + 1;
+    }
+  }
+  X3_HD void finish() {
+    flush();
+    if (cnt) *dst = bswap32((uint32_t)(acc << (32u - cnt)));
+  }
+};
+
+// Fast-path packer.  Rice codewords are at most 10 bits at the default thresholds, so three of them are first
+// merged in a 32-bit register and appended with one 64-bit shift; BFP / literal samples go in pairs.
+X3_HD void block_pack_fast(const FastBlock &fb, uint32_t len, const BlockMode &m, FastSink &sink) {
+  const bool full = len == (uint32_t)kFastBL;
   if (m.kind == kRice) {
-    // codeword = (u>>k) zeros, then 1, then the k low bits of u; at the default thresholds it is at most
-    // 10 bits (RICE1, u<=16), so three codewords fit between flushes (31 + 30 <= 64).
     sink.put(m.hdr, 2);
     const uint32_t k = m.k, marker = 1u << k, mask = marker - 1u, k1 = k + 1u;
 #pragma unroll
-    for (int i = 0; i < kFastBL; i++) {
-      if (i < kFastBL - 1 || len == (uint32_t)kFastBL) {
-        uint32_t u = fb.u[i];
-        sink.put(marker | (u & mask), (u >> k) + k1);
-      }
-      if (i % 3 == 2 || i == kFastBL - 1) sink.flush();
+    for (int t = 0; t < 6; t++) {
+      const uint32_t u0 = fb.u[3 * t], u1 = fb.u[3 * t + 1], u2 = fb.u[3 * t + 2];
+      const uint32_t l2 = (u2 >> k) + k1;
+      const uint32_t l12 = (u1 >> k) + k1 + l2;
+      const uint32_t v = ((marker | (u0 & mask)) << l12) | ((marker | (u1 & mask)) << l2) | (marker | (u2 & mask));
+      sink.put(v, (u0 >> k) + k1 + l12);
+      sink.flush();
+    }
+    {
+      const uint32_t u0 = fb.u[18], u1 = fb.u[19];
+      const uint32_t l1 = full ? (u1 >> k) + k1 : 0u;
+      const uint32_t c1 = full ? (marker | (u1 & mask)) : 0u;
+      sink.put(((marker | (u0 & mask)) << l1) | c1, (u0 >> k) + k1 + l1);
     }
   } else if (m.kind == kBfp) {
     sink.put(m.hdr, 6);
-    sink.flush();  // 31 + 6 + 2*15 would overflow the 64-bit accumulator
+    sink.flush();
     const uint32_t w = m.k + 1u, mask = (1u << w) - 1u;  // w <= 15
 #pragma unroll
-    for (int i = 0; i < kFastBL; i++) {
-      if (i < kFastBL - 1 || len == (uint32_t)kFastBL) sink.put((uint32_t)unfold(fb.u[i]) & mask, w);
-      if (i % 2 == 1) sink.flush();
+    for (int t = 0; t < 10; t++) {
+      const uint32_t d0 = (uint32_t)unfold(fb.u[2 * t]) & mask, d1 = (uint32_t)unfold(fb.u[2 * t + 1]) & mask;
+      if (t < 9 || full) sink.put((d0 << w) | d1, 2u * w);
+      else sink.put(d0, w);
+      sink.flush();
     }
   } else {
     sink.put(15u, 6);
     sink.flush();
     int32_t x = fb.pred;
 #pragma unroll
-    for (int i = 0; i < kFastBL; i++) {
-      if (i < kFastBL - 1 || len == (uint32_t)kFastBL) {
-        x += unfold(fb.u[i]);
-        sink.put((uint32_t)x & 0xffffu, 16);
-      }
-      if (i % 2 == 1) sink.flush();
+    for (int t = 0; t < 10; t++) {
+      x += unfold(fb.u[2 * t]);
+      const uint32_t s0 = (uint32_t)x & 0xffffu;
+      x += unfold(fb.u[2 * t + 1]);
+      if (t < 9 || full) sink.put((s0 << 16) | ((uint32_t)x & 0xffffu), 32);
+      else sink.put(s0, 16);
+      sink.flush();
     }
   }
+  sink.finish();
 }
 
 // payload bytes for a payload of total_bits bits: pad to a byte, then to an even length

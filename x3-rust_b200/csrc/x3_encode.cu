@@ -26,6 +26,7 @@ constexpr int NT = kEncThreads;
 constexpr int NW = NT / 32;
 
 // stage frame f's samples into shared memory (asynchronously where 16-byte alignment allows)
+template <int NTHREADS>
 __device__ __forceinline__ void issue_frame_load(const EncodeArgs &a, uint32_t f, int16_t *s_in) {
   const unsigned long long s0 = (unsigned long long)f * a.P.spf;
   unsigned long long rem = a.n_samples - s0;
@@ -34,15 +35,18 @@ __device__ __forceinline__ void issue_frame_load(const EncodeArgs &a, uint32_t f
   uint32_t done = 0;
   if ((((uintptr_t)src) & 15u) == 0) {
     const uint32_t chunks = n >> 3;  // 8 samples = 16 bytes
-    for (uint32_t c = threadIdx.x; c < chunks; c += NT) cp_async16(s_in + c * 8, src + c * 8);
+    for (uint32_t c = threadIdx.x; c < chunks; c += NTHREADS) cp_async16(s_in + c * 8, src + c * 8);
     done = chunks << 3;
   }
-  for (uint32_t i = done + threadIdx.x; i < n; i += NT) s_in[i] = __ldg(src + i);
+  for (uint32_t i = done + threadIdx.x; i < n; i += NTHREADS) s_in[i] = __ldg(src + i);
   cp_async_commit();
 }
 
-template <bool FAST>
-__global__ void __launch_bounds__(NT, FAST ? 2 : 1) encode_frames_kernel(const EncodeArgs a) {
+// Generic kernel: any Parameters the API accepts (and default Parameters with more than 512 blocks per frame).
+// Same phases as the fast kernel below, but blocks re-read the staged samples and words are merged through the
+// Hs/Ts exchange arrays (x3_enc_core.cuh, BitSink).
+constexpr bool FAST = false;
+__global__ void __launch_bounds__(NT, 1) encode_frames_generic_kernel(const EncodeArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // ---- shared memory carve-up (all offsets 16-byte aligned) ----
   const uint32_t in_bytes = (2u * (a.P.spf + 8u) + 15u) & ~15u;
@@ -69,7 +73,7 @@ __global__ void __launch_bounds__(NT, FAST ? 2 : 1) encode_frames_kernel(const E
   if (tid == 0) s_misc[32] = atomicAdd(a.ticket, 1u);
   __syncthreads();
   uint32_t f = s_misc[32];
-  if (f < a.n_frames) issue_frame_load(a, f, s_in);
+  if (f < a.n_frames) issue_frame_load<NT>(a, f, s_in);
 
   uint32_t full_block_count = 0;  // lane m < 6 of every warp counts full blocks coded in mode m
 
@@ -93,16 +97,11 @@ __global__ void __launch_bounds__(NT, FAST ? 2 : 1) encode_frames_kernel(const E
       if (active && n > start) len = (n - start) < BL ? (n - start) : BL;
 
       // ---- measure ----
-      FastBlock fb;
       BlockMode mode;
       mode.kind = kRice; mode.k = 0; mode.hdr = 0; mode.stat = 0;
       uint32_t nbits = 0;
-      bool use_fast = false;
       if (active) {
-        if (FAST && len >= (uint32_t)kFastBL - 1) {
-          use_fast = true;
-          mode = block_measure_fast(s_in, start, len, fb, nbits);
-        } else if (len > 0) {
+        if (len > 0) {
           mode = block_measure_generic(s_in, start, len, a.P, nbits);
         }
         if (b == 0) nbits += 16;  // <Audio State>: first sample as 16 raw bits, encoder.rs:189
@@ -147,7 +146,7 @@ __global__ void __launch_bounds__(NT, FAST ? 2 : 1) encode_frames_kernel(const E
         // next frame can stream in while this one is packed.  Blocks on the generic path re-read s_in, but
         // they only occur in the stream's final frame, after which there is nothing to prefetch.
         f_next = s_misc[32];
-        if (f_next < a.n_frames) issue_frame_load(a, f_next, s_in);
+        if (f_next < a.n_frames) issue_frame_load<NT>(a, f_next, s_in);
       }
 
       // ---- pack ----
@@ -155,11 +154,10 @@ __global__ void __launch_bounds__(NT, FAST ? 2 : 1) encode_frames_kernel(const E
         BitSink sink;
         sink.init(bit_off, s_words, &s_Hs[b]);
         if (b == 0) {
-          sink.put((uint32_t)(uint16_t)(use_fast ? fb.pred : (int32_t)s_in[0]), 16);
+          sink.put((uint32_t)(uint16_t)s_in[0], 16);
           sink.flush();
         }
-        if (use_fast) block_pack_fast(fb, len, mode, sink);
-        else if (len > 0) block_pack_generic(s_in, start, len, mode, sink);
+        if (len > 0) block_pack_generic(s_in, start, len, mode, sink);
         bool has_tail;
         uint32_t timg = sink.finish(has_tail);
         s_Ts[b] = timg;
@@ -283,12 +281,235 @@ __global__ void __launch_bounds__(NT, FAST ? 2 : 1) encode_frames_kernel(const E
     f = f_next;
     if (!FAST && f < a.n_frames) {
       __syncthreads();  // generic path re-reads s_in while packing, so only now may it be overwritten
-      issue_frame_load(a, f, s_in);
+      issue_frame_load<NT>(a, f, s_in);
     }
   }
 
   // ---- flush statistics ----
   if (lane < 6 && full_block_count) atomicAdd(a.result + 2 + lane, (unsigned long long)full_block_count * BL);
+  __syncthreads();
+  if (tid < 6 && s_misc[40 + tid]) atomicAdd(a.result + 2 + tid, (unsigned long long)s_misc[40 + tid]);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Fast kernel: Parameters::default() and at most 512 blocks per frame.
+// 16 worker warps (one thread per block) + 1 control warp.  Per frame:
+//   (A) samples staged -> workers: measure (diff, fold, max, mode, bits) + warp scan
+//   (B) all: CTA scan finished -> control warp publishes the frame size and runs the decoupled look-back
+//       while the workers prefetch the next frame and pack their blocks (plain stores; a block whose first
+//       bit is not word aligned ORs its first word in with one shared-memory atomic after barrier D)
+//   (D,E workers only) -> per-warp CRC over slices of 32 sixteen-byte chunks (shuffle tree)
+//   (F) all: workers copy the payload out; the control warp folds the slice CRCs, builds the header
+//       (encoder.rs:122-162) and writes its 20 bytes.
+// ------------------------------------------------------------------------------------------------
+constexpr int NTF = kEncFastThreads;      // 544
+constexpr int NWW = 16;                   // worker warps
+constexpr int kMaxSlices = 64;
+
+__device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 1, 512;\n" ::: "memory"); }
+
+__global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const EncodeArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint32_t in_bytes = (2u * (a.P.spf + 8u) + 15u) & ~15u;
+  const uint32_t img_bytes = (32u + 4u * (a.out_words_cap + 8u) + 15u) & ~15u;
+  unsigned char *p = smem_raw;
+  int16_t *s_in = reinterpret_cast<int16_t *>(p);                 p += in_bytes;
+  unsigned char *s_img = p;                                        p += img_bytes;
+  uint16_t *s_crcT = reinterpret_cast<uint16_t *>(p);             p += kCrcTableEntries * 2;
+  uint32_t *s_first = reinterpret_cast<uint32_t *>(p);            p += 512 * 4;
+  uint32_t *s_V = reinterpret_cast<uint32_t *>(p);                p += kMaxSlices * 4;
+  uint32_t *s_misc = reinterpret_cast<uint32_t *>(p);
+  // s_misc: [0..16) warp totals, [32] next ticket, [34..36) out offset (u64), [36] capacity ok, [40..46) stats
+  uint32_t *s_words = reinterpret_cast<uint32_t *>(s_img + 32);   // payload image, 16-byte aligned
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const bool worker = wid < NWW;
+  constexpr uint32_t BL = 20;
+
+  for (int i = tid; i < kCrcTableEntries; i += NTF) s_crcT[i] = a.crc_tables[i];
+  if (tid < 6) s_misc[40 + tid] = 0;
+  if (tid == 0) s_misc[32] = atomicAdd(a.ticket, 1u);
+  __syncthreads();
+  uint32_t f = s_misc[32];
+  if (f < a.n_frames) issue_frame_load<NTF>(a, f, s_in);
+  uint32_t full_block_count = 0;
+
+  while (f < a.n_frames) {
+    const unsigned long long s0 = (unsigned long long)f * a.P.spf;
+    const unsigned long long remn = a.n_samples - s0;
+    const uint32_t n = remn < a.P.spf ? (uint32_t)remn : a.P.spf;
+    const uint32_t nblk = n > 1 ? (n - 2u) / BL + 1u : 1u;  // <= 512
+
+    cp_async_wait_all();
+    __syncthreads();  // (A)
+
+    // ---- workers: measure ----
+    const uint32_t b = tid;
+    const bool active = worker && b < nblk;
+    const uint32_t start = 1u + b * BL;
+    uint32_t len = 0;
+    if (active && n > start) len = (n - start) < BL ? (n - start) : BL;
+    FastBlock fb;
+    BlockMode mode;
+    mode.kind = kRice; mode.k = 0; mode.hdr = 0; mode.stat = 0;
+    uint32_t nbits = 0;
+    bool use_fast = false;
+    if (active) {
+      if (len >= BL - 1) {
+        use_fast = true;
+        mode = block_measure_fast(s_in, start, len, fb, nbits);
+      } else if (len > 0) {
+        mode = block_measure_generic(s_in, start, len, a.P, nbits);  // short last block of the stream's last frame
+      }
+      if (b == 0) nbits += 16;  // <Audio State>, encoder.rs:189
+    }
+    uint32_t incl = nbits;
+    if (worker) {
+      const bool full = active && len == BL;
+#pragma unroll
+      for (int m = 0; m < 6; m++) {
+        const unsigned bal = __ballot_sync(0xffffffffu, full && mode.stat == (uint32_t)m);
+        if (lane == m) full_block_count += __popc(bal);
+      }
+      if (active && len != BL && len > 0) atomicAdd(&s_misc[40 + mode.stat], len);
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      if (lane == 31) s_misc[wid] = incl;
+      if (tid == 0) s_misc[32] = atomicAdd(a.ticket, 1u);  // this CTA's next frame
+    }
+    __syncthreads();  // (B) warp totals visible; all reads of s_in by the fast path are done
+
+    const uint32_t wt = lane < NWW ? s_misc[lane] : 0u;
+    uint32_t wincl = wt;
+#pragma unroll
+    for (int d = 1; d < NWW; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, wincl, d);
+      if (lane >= d) wincl += t;
+    }
+    const uint32_t total_bits = __shfl_sync(0xffffffffu, wincl, NWW - 1);
+    const uint32_t payload_len = payload_bytes(total_bits);
+    const uint32_t frame_bytes = (uint32_t)kFrameHeaderLen + payload_len;
+    const uint32_t f_next = s_misc[32];
+
+    if (!worker) {
+      // ---- control warp: publish the size, then look back for this frame's byte offset ----
+      if (lane == 0) st_status(a.status + f, (f == 0 ? kFlagPrefix : kFlagAgg) | (unsigned long long)frame_bytes);
+      const unsigned long long excl = lookback_exclusive(a.status, f, frame_bytes);
+      if (lane == 0) {
+        s_misc[34] = (uint32_t)excl;
+        s_misc[35] = (uint32_t)(excl >> 32);
+        const bool fits = excl + frame_bytes <= a.out_cap;
+        s_misc[36] = fits ? 1u : 0u;
+        if (!fits) atomicMax(a.result + 1, 1ull);                    // ByteWriterInsufficientMemory, bytewriter.rs:88
+        if (f == a.n_frames - 1) a.result[0] = excl + frame_bytes;   // total stream length
+      }
+    } else {
+      // ---- workers: prefetch the next frame, pack this one ----
+      const uint32_t warp_base = __shfl_sync(0xffffffffu, wincl - wt, wid);
+      const uint32_t bit_off = warp_base + (incl - nbits);
+      if (f_next < a.n_frames) issue_frame_load<512>(a, f_next, s_in);
+      if (active) {
+        FastSink sink;
+        sink.init(bit_off, s_words, &s_first[tid]);
+        if (b == 0) {
+          sink.put((uint32_t)(uint16_t)(use_fast ? fb.pred : (int32_t)s_in[0]), 16);
+          sink.flush();
+        }
+        if (use_fast) {
+          block_pack_fast(fb, len, mode, sink);
+        } else {
+          if (len > 0) block_pack_generic(s_in, start, len, mode, sink);
+          sink.finish();
+        }
+      }
+      bar_workers();  // (D) every plain store done
+      if (active && (bit_off & 31u)) atomicOr(&s_words[bit_off >> 5], s_first[tid]);
+      bar_workers();  // (E) payload image complete
+
+      // ---- CRC of 16-byte chunks, combined per slice of 32 chunks by a shuffle tree.  Slice j covers the
+      // chunks at distance 32j .. 32j+31 from the end; V_j = sum_l x^(128 l) * crc(chunk at distance 32j+l). ----
+      const uint32_t m = payload_len >> 4;
+      const uint32_t nslices = (m + 31u) >> 5;
+      for (uint32_t j = wid; j < nslices; j += NWW) {
+        const uint32_t e = 32u * j + lane;
+        uint32_t h = 0;
+        if (e < m) {
+          const uint32_t c = m - 1u - e;
+          const uint4 q = reinterpret_cast<const uint4 *>(s_words)[c];
+          h = c == 0 ? 0xffffu : 0u;  // chunk 0 carries the CRC's initial value
+          h = crc16_word(s_crcT, h, bswap32(q.x));
+          h = crc16_word(s_crcT, h, bswap32(q.y));
+          h = crc16_word(s_crcT, h, bswap32(q.z));
+          h = crc16_word(s_crcT, h, bswap32(q.w));
+        }
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+          const uint32_t o = __shfl_down_sync(0xffffffffu, h, 1 << k);
+          h ^= crc16_mulc(s_crcT, 6 + 2 * k, o);
+        }
+        if (lane == 0) s_V[j] = h;
+      }
+    }
+    __syncthreads();  // (F) slice CRCs, byte offset ready
+
+    const unsigned long long off = (unsigned long long)s_misc[34] | ((unsigned long long)s_misc[35] << 32);
+    const bool fits = s_misc[36] != 0u;
+    if (!worker) {
+      // ---- control warp: payload CRC = sum_j V_j * x^(4096 j), then the tail, then the header ----
+      uint32_t hw = 0;
+      if (lane == 0) {
+        const uint32_t m = payload_len >> 4;
+        const uint32_t nslices = (m + 31u) >> 5;
+        uint32_t s = 0;
+        for (int j = (int)nslices - 1; j >= 0; j--) s = crc16_mulc(s_crcT, 4, s) ^ s_V[j];
+        if (m == 0) s = 0xffffu;
+        const uint32_t rem = payload_len & 15u;  // even
+        uint32_t wi = m * 4u;
+        for (uint32_t done = 0; done + 4u <= rem; done += 4u) s = crc16_word(s_crcT, s, bswap32(s_words[wi++]));
+        if (rem & 2u) s = crc16_half(s_crcT, s, bswap32(s_words[wi]) >> 16);
+        hw = (header_crc(s_crcT, 1u, n, payload_len) << 16) | (s & 0xffffu);
+      }
+      hw = __shfl_sync(0xffffffffu, hw, 0);
+      if (fits && lane < 10) {
+        // header halfwords, big-endian values (id = 1 for audio frames, encoder.rs:210; time = 0, :148-150)
+        uint32_t v = 0;
+        if (lane == 0) v = kFrameKey;
+        else if (lane == 1) v = 0x0101u;
+        else if (lane == 2) v = n & 0xffffu;
+        else if (lane == 3) v = payload_len & 0xffffu;
+        else if (lane == 8) v = hw >> 16;
+        else if (lane == 9) v = hw & 0xffffu;
+        reinterpret_cast<uint16_t *>(a.out + off)[lane] = (uint16_t)(((v & 0xff) << 8) | (v >> 8));
+      }
+    } else if (fits) {
+      // ---- workers: payload image -> its place in the stream (2-byte aligned destination) ----
+      unsigned char *dst = a.out + off + kFrameHeaderLen;
+      const uint32_t L = payload_len;
+      const uintptr_t al = (uintptr_t)dst & 3u;
+      if (al == 0) {
+        uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
+        const uint32_t nw = L >> 2;
+        for (uint32_t i = tid; i < nw; i += 512) d32[i] = s_words[i];
+        if ((L & 2u) && tid == 0) *reinterpret_cast<uint16_t *>(dst + (nw << 2)) = (uint16_t)(s_words[nw] & 0xffffu);
+      } else if (al == 2) {
+        if (tid == 0) *reinterpret_cast<uint16_t *>(dst) = (uint16_t)(s_words[0] & 0xffffu);
+        uint32_t *d32 = reinterpret_cast<uint32_t *>(dst + 2);
+        const uint32_t nw = (L - 2u) >> 2;
+        for (uint32_t i = tid; i < nw; i += 512) d32[i] = __byte_perm(s_words[i], s_words[i + 1], 0x5432);
+        if (((L - 2u) & 2u) && tid == 0) *reinterpret_cast<uint16_t *>(dst + 2 + (nw << 2)) = (uint16_t)(s_words[nw] >> 16);
+      } else {
+        const unsigned char *sb = reinterpret_cast<const unsigned char *>(s_words);
+        for (uint32_t i = tid; i < L; i += 512) dst[i] = sb[i];
+      }
+    }
+    f = f_next;
+  }
+
+  if (worker && lane < 6 && full_block_count) atomicAdd(a.result + 2 + lane, (unsigned long long)full_block_count * BL);
   __syncthreads();
   if (tid < 6 && s_misc[40 + tid]) atomicAdd(a.result + 2 + tid, (unsigned long long)s_misc[40 + tid]);
 }
@@ -304,16 +525,22 @@ size_t encode_smem_bytes(const CodecParams &P, uint32_t max_blocks, uint32_t out
   return (size_t)in_bytes + img_bytes + kCrcTableEntries * 2 + 3u * arr + chunk + 64u * 4u;
 }
 
+size_t encode_fast_smem_bytes(const CodecParams &P, uint32_t out_words_cap) {
+  const uint32_t in_bytes = (2u * (P.spf + 8u) + 15u) & ~15u;
+  const uint32_t img_bytes = (32u + 4u * (out_words_cap + 8u) + 15u) & ~15u;
+  return (size_t)in_bytes + img_bytes + kCrcTableEntries * 2 + 512u * 4u + kMaxSlices * 4u + 64u * 4u;
+}
+
 cudaError_t launch_encode(const EncodeArgs &a, bool fast, int grid, size_t smem, cudaStream_t stream) {
   cudaError_t e;
   if (fast) {
-    e = cudaFuncSetAttribute(encode_frames_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(encode_frames_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    encode_frames_kernel<true><<<grid, NT, smem, stream>>>(a);
+    encode_frames_fast_kernel<<<grid, NTF, smem, stream>>>(a);
   } else {
-    e = cudaFuncSetAttribute(encode_frames_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(encode_frames_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    encode_frames_kernel<false><<<grid, NT, smem, stream>>>(a);
+    encode_frames_generic_kernel<<<grid, NT, smem, stream>>>(a);
   }
   return cudaGetLastError();
 }
@@ -322,11 +549,11 @@ int encode_occupancy(bool fast, size_t smem) {
   int nb = 0;
   cudaError_t e;
   if (fast) {
-    cudaFuncSetAttribute(encode_frames_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, encode_frames_kernel<true>, NT, smem);
+    cudaFuncSetAttribute(encode_frames_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, encode_frames_fast_kernel, NTF, smem);
   } else {
-    cudaFuncSetAttribute(encode_frames_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, encode_frames_kernel<false>, NT, smem);
+    cudaFuncSetAttribute(encode_frames_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, encode_frames_generic_kernel, NT, smem);
   }
   if (e != cudaSuccess || nb < 1) nb = 1;
   return nb;

@@ -9,7 +9,8 @@
 
 namespace x3 {
 
-constexpr int kEncThreads = 512;
+constexpr int kEncThreads = 512;       // generic kernel
+constexpr int kEncFastThreads = 544;   // fast kernel: 16 worker warps + 1 control warp
 constexpr int kDecThreads = 128;
 constexpr int kScanThreads = 256;
 
@@ -29,6 +30,7 @@ struct EncodeArgs {
 };
 
 size_t encode_smem_bytes(const CodecParams &P, uint32_t max_blocks, uint32_t out_words_cap);
+size_t encode_fast_smem_bytes(const CodecParams &P, uint32_t out_words_cap);
 int encode_occupancy(bool fast, size_t smem);
 cudaError_t launch_encode(const EncodeArgs &a, bool fast, int grid, size_t smem, cudaStream_t stream);
 

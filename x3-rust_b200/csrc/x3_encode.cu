@@ -294,34 +294,82 @@ __global__ void __launch_bounds__(NT, 1) encode_frames_generic_kernel(const Enco
 
 // ------------------------------------------------------------------------------------------------
 // Fast kernel: Parameters::default() and at most 512 blocks per frame.
-// 16 worker warps (one thread per block) + 1 control warp.  Per frame:
-//   (A) samples staged -> workers: measure (diff, fold, max, mode, bits) + warp scan
-//   (B) all: CTA scan finished -> control warp publishes the frame size and runs the decoupled look-back
-//       while the workers prefetch the next frame and pack their blocks (plain stores; a block whose first
-//       bit is not word aligned ORs its first word in with one shared-memory atomic after barrier D)
-//   (D,E workers only) -> per-warp CRC over slices of 32 sixteen-byte chunks (shuffle tree)
-//   (F) all: workers copy the payload out; the control warp folds the slice CRCs, builds the header
-//       (encoder.rs:122-162) and writes its 20 bytes.
+//
+// 16 worker warps (one thread per block) and 1 control warp that runs ASYNCHRONOUSLY: the two sides meet only
+// through named barriers used as producer/consumer signals (bar.arrive / bar.sync), and the frame image is
+// double buffered, so a frame's byte offset (which needs every earlier frame's size: decoupled look-back)
+// has a whole frame time to arrive before anybody waits for it.
+//
+//   workers, frame i:  stage samples -> measure + CTA scan -> [size_ready] -> prefetch next frame, pack into
+//                      image[i&1] (plain stores + one atomicOr per unaligned block) -> per-warp CRC slices
+//                      -> [crc_ready] -> wait [off_ready of frame i-1] and copy frame i-1's payload out.
+//   control, frame i:  wait [size_ready] -> publish size, look back -> wait [crc_ready] -> fold the slice CRCs,
+//                      build and write the 20-byte header (encoder.rs:122-162) -> [off_ready].
 // ------------------------------------------------------------------------------------------------
 constexpr int NTF = kEncFastThreads;      // 544
 constexpr int NWW = 16;                   // worker warps
 constexpr int kMaxSlices = 64;
+constexpr uint32_t kNoFrame = 0xffffffffu;
 
 __device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 1, 512;\n" ::: "memory"); }
+// barrier ids are immediates so that ptxas reserves exactly the eight barriers used (not all sixteen)
+__device__ __forceinline__ void bar_sync_all(int id) {
+  switch (id) {
+    case 2: asm volatile("bar.sync 2, 544;\n" ::: "memory"); break;
+    case 3: asm volatile("bar.sync 3, 544;\n" ::: "memory"); break;
+    case 4: asm volatile("bar.sync 4, 544;\n" ::: "memory"); break;
+    case 5: asm volatile("bar.sync 5, 544;\n" ::: "memory"); break;
+    case 6: asm volatile("bar.sync 6, 544;\n" ::: "memory"); break;
+    default: asm volatile("bar.sync 7, 544;\n" ::: "memory"); break;
+  }
+}
+__device__ __forceinline__ void bar_arrive_all(int id) {
+  __threadfence_block();
+  switch (id) {
+    case 2: asm volatile("bar.arrive 2, 544;\n" ::: "memory"); break;
+    case 3: asm volatile("bar.arrive 3, 544;\n" ::: "memory"); break;
+    case 4: asm volatile("bar.arrive 4, 544;\n" ::: "memory"); break;
+    case 5: asm volatile("bar.arrive 5, 544;\n" ::: "memory"); break;
+    case 6: asm volatile("bar.arrive 6, 544;\n" ::: "memory"); break;
+    default: asm volatile("bar.arrive 7, 544;\n" ::: "memory"); break;
+  }
+}
+constexpr int kBarSize = 2, kBarCrc = 4, kBarOff = 6;  // + parity
+
+__device__ __forceinline__ void copy_payload_out(unsigned char *dst, const uint32_t *s_words, uint32_t L, int tid) {
+  // dst is 2-byte aligned; s_words is the 16-byte aligned payload image
+  const uintptr_t al = (uintptr_t)dst & 3u;
+  if (al == 0) {
+    uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
+    const uint32_t nw = L >> 2;
+    for (uint32_t i = tid; i < nw; i += 512) d32[i] = s_words[i];
+    if ((L & 2u) && tid == 0) *reinterpret_cast<uint16_t *>(dst + (nw << 2)) = (uint16_t)(s_words[nw] & 0xffffu);
+  } else if (al == 2) {
+    if (tid == 0) *reinterpret_cast<uint16_t *>(dst) = (uint16_t)(s_words[0] & 0xffffu);
+    uint32_t *d32 = reinterpret_cast<uint32_t *>(dst + 2);
+    const uint32_t nw = (L - 2u) >> 2;
+    for (uint32_t i = tid; i < nw; i += 512) d32[i] = __byte_perm(s_words[i], s_words[i + 1], 0x5432);
+    if (((L - 2u) & 2u) && tid == 0) *reinterpret_cast<uint16_t *>(dst + 2 + (nw << 2)) = (uint16_t)(s_words[nw] >> 16);
+  } else {
+    const unsigned char *sb = reinterpret_cast<const unsigned char *>(s_words);
+    for (uint32_t i = tid; i < L; i += 512) dst[i] = sb[i];
+  }
+}
 
 __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const EncodeArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t in_bytes = (2u * (a.P.spf + 8u) + 15u) & ~15u;
-  const uint32_t img_bytes = (32u + 4u * (a.out_words_cap + 8u) + 15u) & ~15u;
+  const uint32_t img_bytes = (4u * (a.out_words_cap + 8u) + 15u) & ~15u;
   unsigned char *p = smem_raw;
   int16_t *s_in = reinterpret_cast<int16_t *>(p);                 p += in_bytes;
-  unsigned char *s_img = p;                                        p += img_bytes;
+  uint32_t *s_img0 = reinterpret_cast<uint32_t *>(p);             p += img_bytes;
+  uint32_t *s_img1 = reinterpret_cast<uint32_t *>(p);             p += img_bytes;
   uint16_t *s_crcT = reinterpret_cast<uint16_t *>(p);             p += kCrcTableEntries * 2;
   uint32_t *s_first = reinterpret_cast<uint32_t *>(p);            p += 512 * 4;
-  uint32_t *s_V = reinterpret_cast<uint32_t *>(p);                p += kMaxSlices * 4;
+  uint32_t *s_V = reinterpret_cast<uint32_t *>(p);                p += 2 * kMaxSlices * 4;
   uint32_t *s_misc = reinterpret_cast<uint32_t *>(p);
-  // s_misc: [0..16) warp totals, [32] next ticket, [34..36) out offset (u64), [36] capacity ok, [40..46) stats
-  uint32_t *s_words = reinterpret_cast<uint32_t *>(s_img + 32);   // payload image, 16-byte aligned
+  // s_misc: [0..16) warp totals, [32] next ticket, [40..46) stats of short blocks,
+  //         per parity q at [48+8q ..): +0 frame, +1 samples, +2 payload_len, +4,+5 byte offset, +6 fits
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const bool worker = wid < NWW;
@@ -329,24 +377,85 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
 
   for (int i = tid; i < kCrcTableEntries; i += NTF) s_crcT[i] = a.crc_tables[i];
   if (tid < 6) s_misc[40 + tid] = 0;
-  if (tid == 0) s_misc[32] = atomicAdd(a.ticket, 1u);
   __syncthreads();
-  uint32_t f = s_misc[32];
-  if (f < a.n_frames) issue_frame_load<NTF>(a, f, s_in);
+  // Frames are dealt round-robin: CTA c takes frames c, c+G, c+2G, ...  (the grid is sized so that every CTA
+  // is resident).  A frame's predecessors are then being worked on at the same time as the frame itself, which
+  // keeps the look-back short; handing frames out early through an atomic ticket (to prefetch them) leaves
+  // ticketed-but-unmeasured predecessors in the window for a whole frame time.
+
+  if (!worker) {
+    // ================================ control warp ================================
+    for (uint32_t par = 0;; par ^= 1u) {
+      uint32_t *info = s_misc + 48 + 8 * par;
+      bar_sync_all(kBarSize + par);
+      const uint32_t f = info[0];
+      if (f == kNoFrame) break;
+      const uint32_t n = info[1], payload_len = info[2];
+      const uint32_t frame_bytes = (uint32_t)kFrameHeaderLen + payload_len;
+      const unsigned long long excl = lookback_exclusive(a.status, f, frame_bytes);
+      const bool fits = excl + frame_bytes <= a.out_cap;
+      if (lane == 0) {
+        if (!fits) atomicMax(a.result + 1, 1ull);                    // ByteWriterInsufficientMemory, bytewriter.rs:88
+        if (f == a.n_frames - 1) a.result[0] = excl + frame_bytes;   // total stream length
+      }
+      bar_sync_all(kBarCrc + par);
+      // payload CRC = sum_j V_j * x^(4096 j), then the tail bytes, then the header
+      const uint32_t *s_words = par ? s_img1 : s_img0;
+      const uint32_t *V = s_V + par * kMaxSlices;
+      uint32_t hw = 0;
+      if (lane == 0) {
+        const uint32_t m = payload_len >> 4;
+        const uint32_t nslices = (m + 31u) >> 5;
+        uint32_t s = 0;
+        for (int j = (int)nslices - 1; j >= 0; j--) s = crc16_mulc(s_crcT, 4, s) ^ V[j];
+        if (m == 0) s = 0xffffu;
+        const uint32_t rem = payload_len & 15u;  // even
+        uint32_t wi = m * 4u;
+        for (uint32_t done = 0; done + 4u <= rem; done += 4u) s = crc16_word(s_crcT, s, bswap32(s_words[wi++]));
+        if (rem & 2u) s = crc16_half(s_crcT, s, bswap32(s_words[wi]) >> 16);
+        hw = (header_crc(s_crcT, 1u, n, payload_len) << 16) | (s & 0xffffu);
+        info[4] = (uint32_t)excl;
+        info[5] = (uint32_t)(excl >> 32);
+        info[6] = fits ? 1u : 0u;
+      }
+      hw = __shfl_sync(0xffffffffu, hw, 0);
+      if (fits && lane < 10) {
+        // header halfwords, big-endian values (id = 1 for audio frames, encoder.rs:210; time = 0, :148-150)
+        uint32_t v = 0;
+        if (lane == 0) v = kFrameKey;
+        else if (lane == 1) v = 0x0101u;
+        else if (lane == 2) v = n & 0xffffu;
+        else if (lane == 3) v = payload_len & 0xffffu;
+        else if (lane == 8) v = hw >> 16;
+        else if (lane == 9) v = hw & 0xffffu;
+        reinterpret_cast<uint16_t *>(a.out + excl)[lane] = (uint16_t)(((v & 0xff) << 8) | (v >> 8));
+      }
+      __syncwarp();
+      bar_arrive_all(kBarOff + par);
+    }
+    return;
+  }
+
+  // ================================== workers ==================================
+  uint32_t f = blockIdx.x;
+  if (f < a.n_frames) issue_frame_load<512>(a, f, s_in);
   uint32_t full_block_count = 0;
+  uint32_t it = 0, prev_payload_len = 0;
 
   while (f < a.n_frames) {
+    const uint32_t par = it & 1u;
+    uint32_t *s_words = par ? s_img1 : s_img0;
     const unsigned long long s0 = (unsigned long long)f * a.P.spf;
     const unsigned long long remn = a.n_samples - s0;
     const uint32_t n = remn < a.P.spf ? (uint32_t)remn : a.P.spf;
     const uint32_t nblk = n > 1 ? (n - 2u) / BL + 1u : 1u;  // <= 512
 
     cp_async_wait_all();
-    __syncthreads();  // (A)
+    bar_workers();  // (A) samples staged
 
-    // ---- workers: measure ----
+    // ---- measure ----
     const uint32_t b = tid;
-    const bool active = worker && b < nblk;
+    const bool active = b < nblk;
     const uint32_t start = 1u + b * BL;
     uint32_t len = 0;
     if (active && n > start) len = (n - start) < BL ? (n - start) : BL;
@@ -364,8 +473,7 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
       }
       if (b == 0) nbits += 16;  // <Audio State>, encoder.rs:189
     }
-    uint32_t incl = nbits;
-    if (worker) {
+    {
       const bool full = active && len == BL;
 #pragma unroll
       for (int m = 0; m < 6; m++) {
@@ -373,15 +481,15 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
         if (lane == m) full_block_count += __popc(bal);
       }
       if (active && len != BL && len > 0) atomicAdd(&s_misc[40 + mode.stat], len);
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
-      }
-      if (lane == 31) s_misc[wid] = incl;
-      if (tid == 0) s_misc[32] = atomicAdd(a.ticket, 1u);  // this CTA's next frame
     }
-    __syncthreads();  // (B) warp totals visible; all reads of s_in by the fast path are done
+    uint32_t incl = nbits;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_misc[wid] = incl;
+    bar_workers();  // (B) warp totals visible; all reads of s_in by the fast path are done
 
     const uint32_t wt = lane < NWW ? s_misc[lane] : 0u;
     uint32_t wincl = wt;
@@ -392,48 +500,43 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
     }
     const uint32_t total_bits = __shfl_sync(0xffffffffu, wincl, NWW - 1);
     const uint32_t payload_len = payload_bytes(total_bits);
-    const uint32_t frame_bytes = (uint32_t)kFrameHeaderLen + payload_len;
-    const uint32_t f_next = s_misc[32];
+    const uint32_t f_next = f + gridDim.x < a.n_frames ? f + gridDim.x : kNoFrame;
+    if (tid == 0) {
+      uint32_t *info = s_misc + 48 + 8 * par;
+      info[0] = f; info[1] = n; info[2] = payload_len;
+      // publish the frame size right away (the control warp may still be busy with the previous frame)
+      st_status(a.status + f, (f == 0 ? kFlagPrefix : kFlagAgg) | (unsigned long long)(kFrameHeaderLen + payload_len));
+    }
+    bar_arrive_all(kBarSize + par);  // -> control: frame size known
 
-    if (!worker) {
-      // ---- control warp: publish the size, then look back for this frame's byte offset ----
-      if (lane == 0) st_status(a.status + f, (f == 0 ? kFlagPrefix : kFlagAgg) | (unsigned long long)frame_bytes);
-      const unsigned long long excl = lookback_exclusive(a.status, f, frame_bytes);
-      if (lane == 0) {
-        s_misc[34] = (uint32_t)excl;
-        s_misc[35] = (uint32_t)(excl >> 32);
-        const bool fits = excl + frame_bytes <= a.out_cap;
-        s_misc[36] = fits ? 1u : 0u;
-        if (!fits) atomicMax(a.result + 1, 1ull);                    // ByteWriterInsufficientMemory, bytewriter.rs:88
-        if (f == a.n_frames - 1) a.result[0] = excl + frame_bytes;   // total stream length
+    // ---- prefetch the next frame, pack this one ----
+    const uint32_t warp_base = __shfl_sync(0xffffffffu, wincl - wt, wid);
+    const uint32_t bit_off = warp_base + (incl - nbits);
+    if (f_next < a.n_frames) issue_frame_load<512>(a, f_next, s_in);
+    if (active) {
+      FastSink sink;
+      sink.init(bit_off, s_words, &s_first[tid]);
+      if (b == 0) {
+        sink.put((uint32_t)(uint16_t)(use_fast ? fb.pred : (int32_t)s_in[0]), 16);
+        sink.flush();
       }
-    } else {
-      // ---- workers: prefetch the next frame, pack this one ----
-      const uint32_t warp_base = __shfl_sync(0xffffffffu, wincl - wt, wid);
-      const uint32_t bit_off = warp_base + (incl - nbits);
-      if (f_next < a.n_frames) issue_frame_load<512>(a, f_next, s_in);
-      if (active) {
-        FastSink sink;
-        sink.init(bit_off, s_words, &s_first[tid]);
-        if (b == 0) {
-          sink.put((uint32_t)(uint16_t)(use_fast ? fb.pred : (int32_t)s_in[0]), 16);
-          sink.flush();
-        }
-        if (use_fast) {
-          block_pack_fast(fb, len, mode, sink);
-        } else {
-          if (len > 0) block_pack_generic(s_in, start, len, mode, sink);
-          sink.finish();
-        }
+      if (use_fast) {
+        block_pack_fast(fb, len, mode, sink);
+      } else {
+        if (len > 0) block_pack_generic(s_in, start, len, mode, sink);
+        sink.finish();
       }
-      bar_workers();  // (D) every plain store done
-      if (active && (bit_off & 31u)) atomicOr(&s_words[bit_off >> 5], s_first[tid]);
-      bar_workers();  // (E) payload image complete
+    }
+    bar_workers();  // (D) every plain store done
+    if (active && (bit_off & 31u)) atomicOr(&s_words[bit_off >> 5], s_first[tid]);
+    bar_workers();  // (E) payload image complete
 
-      // ---- CRC of 16-byte chunks, combined per slice of 32 chunks by a shuffle tree.  Slice j covers the
-      // chunks at distance 32j .. 32j+31 from the end; V_j = sum_l x^(128 l) * crc(chunk at distance 32j+l). ----
+    // ---- CRC of 16-byte chunks, combined per slice of 32 chunks by a shuffle tree.  Slice j covers the
+    // chunks at distance 32j .. 32j+31 from the end; V_j = sum_l x^(128 l) * crc(chunk at distance 32j+l). ----
+    {
       const uint32_t m = payload_len >> 4;
       const uint32_t nslices = (m + 31u) >> 5;
+      uint32_t *V = s_V + par * kMaxSlices;
       for (uint32_t j = wid; j < nslices; j += NWW) {
         const uint32_t e = 32u * j + lane;
         uint32_t h = 0;
@@ -451,66 +554,42 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
           const uint32_t o = __shfl_down_sync(0xffffffffu, h, 1 << k);
           h ^= crc16_mulc(s_crcT, 6 + 2 * k, o);
         }
-        if (lane == 0) s_V[j] = h;
+        if (lane == 0) V[j] = h;
       }
     }
-    __syncthreads();  // (F) slice CRCs, byte offset ready
+    bar_arrive_all(kBarCrc + par);  // -> control: slice CRCs and image complete
 
-    const unsigned long long off = (unsigned long long)s_misc[34] | ((unsigned long long)s_misc[35] << 32);
-    const bool fits = s_misc[36] != 0u;
-    if (!worker) {
-      // ---- control warp: payload CRC = sum_j V_j * x^(4096 j), then the tail, then the header ----
-      uint32_t hw = 0;
-      if (lane == 0) {
-        const uint32_t m = payload_len >> 4;
-        const uint32_t nslices = (m + 31u) >> 5;
-        uint32_t s = 0;
-        for (int j = (int)nslices - 1; j >= 0; j--) s = crc16_mulc(s_crcT, 4, s) ^ s_V[j];
-        if (m == 0) s = 0xffffu;
-        const uint32_t rem = payload_len & 15u;  // even
-        uint32_t wi = m * 4u;
-        for (uint32_t done = 0; done + 4u <= rem; done += 4u) s = crc16_word(s_crcT, s, bswap32(s_words[wi++]));
-        if (rem & 2u) s = crc16_half(s_crcT, s, bswap32(s_words[wi]) >> 16);
-        hw = (header_crc(s_crcT, 1u, n, payload_len) << 16) | (s & 0xffffu);
-      }
-      hw = __shfl_sync(0xffffffffu, hw, 0);
-      if (fits && lane < 10) {
-        // header halfwords, big-endian values (id = 1 for audio frames, encoder.rs:210; time = 0, :148-150)
-        uint32_t v = 0;
-        if (lane == 0) v = kFrameKey;
-        else if (lane == 1) v = 0x0101u;
-        else if (lane == 2) v = n & 0xffffu;
-        else if (lane == 3) v = payload_len & 0xffffu;
-        else if (lane == 8) v = hw >> 16;
-        else if (lane == 9) v = hw & 0xffffu;
-        reinterpret_cast<uint16_t *>(a.out + off)[lane] = (uint16_t)(((v & 0xff) << 8) | (v >> 8));
-      }
-    } else if (fits) {
-      // ---- workers: payload image -> its place in the stream (2-byte aligned destination) ----
-      unsigned char *dst = a.out + off + kFrameHeaderLen;
-      const uint32_t L = payload_len;
-      const uintptr_t al = (uintptr_t)dst & 3u;
-      if (al == 0) {
-        uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
-        const uint32_t nw = L >> 2;
-        for (uint32_t i = tid; i < nw; i += 512) d32[i] = s_words[i];
-        if ((L & 2u) && tid == 0) *reinterpret_cast<uint16_t *>(dst + (nw << 2)) = (uint16_t)(s_words[nw] & 0xffffu);
-      } else if (al == 2) {
-        if (tid == 0) *reinterpret_cast<uint16_t *>(dst) = (uint16_t)(s_words[0] & 0xffffu);
-        uint32_t *d32 = reinterpret_cast<uint32_t *>(dst + 2);
-        const uint32_t nw = (L - 2u) >> 2;
-        for (uint32_t i = tid; i < nw; i += 512) d32[i] = __byte_perm(s_words[i], s_words[i + 1], 0x5432);
-        if (((L - 2u) & 2u) && tid == 0) *reinterpret_cast<uint16_t *>(dst + 2 + (nw << 2)) = (uint16_t)(s_words[nw] >> 16);
-      } else {
-        const unsigned char *sb = reinterpret_cast<const unsigned char *>(s_words);
-        for (uint32_t i = tid; i < L; i += 512) dst[i] = sb[i];
+    // ---- the previous frame's payload goes out now: its offset has had a whole frame time to arrive ----
+    if (it > 0) {
+      const uint32_t q = par ^ 1u;
+      bar_sync_all(kBarOff + q);
+      const uint32_t *info = s_misc + 48 + 8 * q;
+      if (info[6]) {
+        const unsigned long long off = (unsigned long long)info[4] | ((unsigned long long)info[5] << 32);
+        copy_payload_out(a.out + off + kFrameHeaderLen, q ? s_img1 : s_img0, prev_payload_len, tid);
       }
     }
+    prev_payload_len = payload_len;
     f = f_next;
+    it++;
   }
-
-  if (worker && lane < 6 && full_block_count) atomicAdd(a.result + 2 + lane, (unsigned long long)full_block_count * BL);
-  __syncthreads();
+  // ---- drain: last frame's payload, then tell the control warp to stop ----
+  if (it > 0) {
+    const uint32_t q = (it - 1u) & 1u;
+    bar_sync_all(kBarOff + q);
+    const uint32_t *info = s_misc + 48 + 8 * q;
+    if (info[6]) {
+      const unsigned long long off = (unsigned long long)info[4] | ((unsigned long long)info[5] << 32);
+      copy_payload_out(a.out + off + kFrameHeaderLen, q ? s_img1 : s_img0, prev_payload_len, tid);
+    }
+  }
+  {
+    const uint32_t par = it & 1u;
+    if (tid == 0) s_misc[48 + 8 * par] = kNoFrame;
+    bar_arrive_all(kBarSize + par);
+  }
+  if (lane < 6 && full_block_count) atomicAdd(a.result + 2 + lane, (unsigned long long)full_block_count * BL);
+  bar_workers();
   if (tid < 6 && s_misc[40 + tid]) atomicAdd(a.result + 2 + tid, (unsigned long long)s_misc[40 + tid]);
 }
 
@@ -527,8 +606,8 @@ size_t encode_smem_bytes(const CodecParams &P, uint32_t max_blocks, uint32_t out
 
 size_t encode_fast_smem_bytes(const CodecParams &P, uint32_t out_words_cap) {
   const uint32_t in_bytes = (2u * (P.spf + 8u) + 15u) & ~15u;
-  const uint32_t img_bytes = (32u + 4u * (out_words_cap + 8u) + 15u) & ~15u;
-  return (size_t)in_bytes + img_bytes + kCrcTableEntries * 2 + 512u * 4u + kMaxSlices * 4u + 64u * 4u;
+  const uint32_t img_bytes = (4u * (out_words_cap + 8u) + 15u) & ~15u;
+  return (size_t)in_bytes + 2u * img_bytes + kCrcTableEntries * 2 + 512u * 4u + 2u * kMaxSlices * 4u + 64u * 4u;
 }
 
 cudaError_t launch_encode(const EncodeArgs &a, bool fast, int grid, size_t smem, cudaStream_t stream) {

@@ -310,6 +310,7 @@ constexpr int NTF = kEncFastThreads;      // 544
 constexpr int NWW = 16;                   // worker warps
 constexpr int kMaxSlices = 64;
 constexpr uint32_t kNoFrame = 0xffffffffu;
+constexpr uint32_t NB = 3;                // frame images in flight per CTA (slack for the look-back: NB-1 frames)
 
 __device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 1, 512;\n" ::: "memory"); }
 // barrier ids are immediates so that ptxas reserves exactly the eight barriers used (not all sixteen)
@@ -320,7 +321,10 @@ __device__ __forceinline__ void bar_sync_all(int id) {
     case 4: asm volatile("bar.sync 4, 544;\n" ::: "memory"); break;
     case 5: asm volatile("bar.sync 5, 544;\n" ::: "memory"); break;
     case 6: asm volatile("bar.sync 6, 544;\n" ::: "memory"); break;
-    default: asm volatile("bar.sync 7, 544;\n" ::: "memory"); break;
+    case 7: asm volatile("bar.sync 7, 544;\n" ::: "memory"); break;
+    case 8: asm volatile("bar.sync 8, 544;\n" ::: "memory"); break;
+    case 9: asm volatile("bar.sync 9, 544;\n" ::: "memory"); break;
+    default: asm volatile("bar.sync 10, 544;\n" ::: "memory"); break;
   }
 }
 __device__ __forceinline__ void bar_arrive_all(int id) {
@@ -331,10 +335,13 @@ __device__ __forceinline__ void bar_arrive_all(int id) {
     case 4: asm volatile("bar.arrive 4, 544;\n" ::: "memory"); break;
     case 5: asm volatile("bar.arrive 5, 544;\n" ::: "memory"); break;
     case 6: asm volatile("bar.arrive 6, 544;\n" ::: "memory"); break;
-    default: asm volatile("bar.arrive 7, 544;\n" ::: "memory"); break;
+    case 7: asm volatile("bar.arrive 7, 544;\n" ::: "memory"); break;
+    case 8: asm volatile("bar.arrive 8, 544;\n" ::: "memory"); break;
+    case 9: asm volatile("bar.arrive 9, 544;\n" ::: "memory"); break;
+    default: asm volatile("bar.arrive 10, 544;\n" ::: "memory"); break;
   }
 }
-constexpr int kBarSize = 2, kBarCrc = 4, kBarOff = 6;  // + parity
+constexpr int kBarSize = 2, kBarCrc = 5, kBarOff = 8;  // + buffer index (0..NB-1)
 
 __device__ __forceinline__ void copy_payload_out(unsigned char *dst, const uint32_t *s_words, uint32_t L, int tid) {
   // dst is 2-byte aligned; s_words is the 16-byte aligned payload image
@@ -362,11 +369,11 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
   const uint32_t img_bytes = (4u * (a.out_words_cap + 8u) + 15u) & ~15u;
   unsigned char *p = smem_raw;
   int16_t *s_in = reinterpret_cast<int16_t *>(p);                 p += in_bytes;
-  uint32_t *s_img0 = reinterpret_cast<uint32_t *>(p);             p += img_bytes;
-  uint32_t *s_img1 = reinterpret_cast<uint32_t *>(p);             p += img_bytes;
+  uint32_t *s_img = reinterpret_cast<uint32_t *>(p);              p += NB * img_bytes;
+  const uint32_t img_words = img_bytes >> 2;
   uint16_t *s_crcT = reinterpret_cast<uint16_t *>(p);             p += kCrcTableEntries * 2;
   uint32_t *s_first = reinterpret_cast<uint32_t *>(p);            p += 512 * 4;
-  uint32_t *s_V = reinterpret_cast<uint32_t *>(p);                p += 2 * kMaxSlices * 4;
+  uint32_t *s_V = reinterpret_cast<uint32_t *>(p);                p += NB * kMaxSlices * 4;
   uint32_t *s_misc = reinterpret_cast<uint32_t *>(p);
   // s_misc: [0..16) warp totals, [32] next ticket, [40..46) stats of short blocks,
   //         per parity q at [48+8q ..): +0 frame, +1 samples, +2 payload_len, +4,+5 byte offset, +6 fits
@@ -385,7 +392,7 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
 
   if (!worker) {
     // ================================ control warp ================================
-    for (uint32_t par = 0;; par ^= 1u) {
+    for (uint32_t par = 0;; par = (par + 1u == NB ? 0u : par + 1u)) {
       uint32_t *info = s_misc + 48 + 8 * par;
       bar_sync_all(kBarSize + par);
       const uint32_t f = info[0];
@@ -400,7 +407,7 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
       }
       bar_sync_all(kBarCrc + par);
       // payload CRC = sum_j V_j * x^(4096 j), then the tail bytes, then the header
-      const uint32_t *s_words = par ? s_img1 : s_img0;
+      const uint32_t *s_words = s_img + par * img_words;
       const uint32_t *V = s_V + par * kMaxSlices;
       uint32_t hw = 0;
       if (lane == 0) {
@@ -440,11 +447,13 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
   uint32_t f = blockIdx.x;
   if (f < a.n_frames) issue_frame_load<512>(a, f, s_in);
   uint32_t full_block_count = 0;
-  uint32_t it = 0, prev_payload_len = 0;
+  uint32_t it = 0, par = 0;
+  uint32_t hist_len[NB];  // payload lengths of the frames still held in the image ring
+#pragma unroll
+  for (uint32_t q = 0; q < NB; q++) hist_len[q] = 0;
 
   while (f < a.n_frames) {
-    const uint32_t par = it & 1u;
-    uint32_t *s_words = par ? s_img1 : s_img0;
+    uint32_t *s_words = s_img + par * img_words;
     const unsigned long long s0 = (unsigned long long)f * a.P.spf;
     const unsigned long long remn = a.n_samples - s0;
     const uint32_t n = remn < a.P.spf ? (uint32_t)remn : a.P.spf;
@@ -559,32 +568,44 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
     }
     bar_arrive_all(kBarCrc + par);  // -> control: slice CRCs and image complete
 
-    // ---- the previous frame's payload goes out now: its offset has had a whole frame time to arrive ----
-    if (it > 0) {
-      const uint32_t q = par ^ 1u;
+    // ---- the oldest frame in the ring goes out now: its offset has had NB-1 frame times to arrive ----
+#pragma unroll
+    for (uint32_t q = 0; q < NB; q++)
+      if (q == par) hist_len[q] = payload_len;
+    if (it >= NB - 1) {
+      const uint32_t q = par + 1u == NB ? 0u : par + 1u;  // the buffer the next frame will reuse
       bar_sync_all(kBarOff + q);
       const uint32_t *info = s_misc + 48 + 8 * q;
+      uint32_t L = 0;
+#pragma unroll
+      for (uint32_t k = 0; k < NB; k++)
+        if (k == q) L = hist_len[k];
       if (info[6]) {
         const unsigned long long off = (unsigned long long)info[4] | ((unsigned long long)info[5] << 32);
-        copy_payload_out(a.out + off + kFrameHeaderLen, q ? s_img1 : s_img0, prev_payload_len, tid);
+        copy_payload_out(a.out + off + kFrameHeaderLen, s_img + q * img_words, L, tid);
       }
     }
-    prev_payload_len = payload_len;
     f = f_next;
     it++;
+    par = par + 1u == NB ? 0u : par + 1u;
   }
-  // ---- drain: last frame's payload, then tell the control warp to stop ----
-  if (it > 0) {
-    const uint32_t q = (it - 1u) & 1u;
-    bar_sync_all(kBarOff + q);
-    const uint32_t *info = s_misc + 48 + 8 * q;
-    if (info[6]) {
-      const unsigned long long off = (unsigned long long)info[4] | ((unsigned long long)info[5] << 32);
-      copy_payload_out(a.out + off + kFrameHeaderLen, q ? s_img1 : s_img0, prev_payload_len, tid);
-    }
-  }
+  // ---- drain: the frames still in the ring, oldest first, then tell the control warp to stop ----
   {
-    const uint32_t par = it & 1u;
+    const uint32_t pending = it < NB - 1 ? it : NB - 1;
+    uint32_t q = (par + NB - pending) % NB;
+    for (uint32_t d = 0; d < pending; d++) {
+      bar_sync_all(kBarOff + q);
+      const uint32_t *info = s_misc + 48 + 8 * q;
+      uint32_t L = 0;
+#pragma unroll
+      for (uint32_t k = 0; k < NB; k++)
+        if (k == q) L = hist_len[k];
+      if (info[6]) {
+        const unsigned long long off = (unsigned long long)info[4] | ((unsigned long long)info[5] << 32);
+        copy_payload_out(a.out + off + kFrameHeaderLen, s_img + q * img_words, L, tid);
+      }
+      q = q + 1u == NB ? 0u : q + 1u;
+    }
     if (tid == 0) s_misc[48 + 8 * par] = kNoFrame;
     bar_arrive_all(kBarSize + par);
   }
@@ -607,7 +628,7 @@ size_t encode_smem_bytes(const CodecParams &P, uint32_t max_blocks, uint32_t out
 size_t encode_fast_smem_bytes(const CodecParams &P, uint32_t out_words_cap) {
   const uint32_t in_bytes = (2u * (P.spf + 8u) + 15u) & ~15u;
   const uint32_t img_bytes = (4u * (out_words_cap + 8u) + 15u) & ~15u;
-  return (size_t)in_bytes + 2u * img_bytes + kCrcTableEntries * 2 + 512u * 4u + 2u * kMaxSlices * 4u + 64u * 4u;
+  return (size_t)in_bytes + NB * img_bytes + kCrcTableEntries * 2 + 512u * 4u + NB * kMaxSlices * 4u + 96u * 4u;
 }
 
 cudaError_t launch_encode(const EncodeArgs &a, bool fast, int grid, size_t smem, cudaStream_t stream) {

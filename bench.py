@@ -179,6 +179,7 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     pkg = importlib.import_module("x3-rust_b200")
     dev = importlib.import_module("x3-rust_b200.device")
+    sharding = importlib.import_module("x3-rust_b200.sharding")
     params = pkg.x3.Parameters.default()
     L = pkg._lib.lib()
 
@@ -206,17 +207,17 @@ def main():
     stream = torch.empty(bound, dtype=torch.uint8, device=device)
     dec = torch.empty(n, dtype=torch.int16, device=device)
 
-    sizes = torch.zeros(world, dtype=torch.int64, device=device)
+    shard_sizes = [0] * world
 
     def step():
+        nonlocal shard_sizes
         _, length, stats = dev.encode_tensor(pcm, params, out=stream)
         enc_ms = dev.last_kernel_ms()
         _, ns, res, code = dev.decode_tensor(stream, length, params, out=dec)
         dec_ms = dev.last_kernel_ms()
         assert code == 0 and ns == n, (code, ns)
         if world > 1:
-            mine = torch.tensor([length], dtype=torch.int64, device=device)
-            dist.all_gather_into_tensor(sizes, mine)     # the only exchange: per-shard compressed sizes
+            shard_sizes, _base = sharding.exchange_sizes(length, dist, device)   # the only exchange (NCCL all-gather)
         return length, enc_ms, dec_ms, stats
 
     def barrier():
@@ -339,7 +340,7 @@ def main():
         "decode_msamples_s": n / (dec_ms + crc_ms + idx_ms) / 1e3 * world,
         "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": int(launches), "clocks": sampler.summary(),
-        "mode_stats": stats, "shard_sizes": [int(x) for x in sizes.tolist()] if world > 1 else [int(length)],
+        "mode_stats": stats, "shard_sizes": shard_sizes if world > 1 else [int(length)],
     }
     print(json.dumps(line))
     if world > 1:

@@ -293,3 +293,29 @@ def test_library_api_forms(pkg, oracle):
     with pytest.raises(pkg.X3Error) as e:
         pkg.encoder.encode([ch, ch], pkg.bytewriter.SliceByteWriter(bytearray(10)), quiet=True)
     assert e.value.code == pkg.error.MORE_THAN_ONE_CHANNEL
+
+
+def test_cpp_cli_round_trip(pkg, oracle, tmp_path):
+    """The compiled host layer (x3-rust_b200/host/x3.hpp + x3_cli.cpp, the reference's `x3 -i -o` CLI)."""
+    import subprocess
+    import wave
+    exe = os.path.join(ROOT, "x3-rust_b200", "host", "x3")
+    assert os.path.exists(exe), "build the CLI with python x3-rust_b200/build.py"
+    pcm = oracle.synth(2, 0x58330002, 384000, 384000 * 3 - 30000, 77777)
+    wav_in, x3a, wav_out = tmp_path / "in.wav", tmp_path / "a.x3a", tmp_path / "out.wav"
+    with wave.open(str(wav_in), "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(384000); w.writeframes(pcm.tobytes())
+    r = subprocess.run([exe, "-i", str(wav_in), "-o", str(x3a)], capture_output=True, text=True)
+    assert r.returncode == 0 and "Rice-3" in r.stdout, r.stderr
+    ref, _ = oracle.x3a_encode(pcm, 384000)
+    assert x3a.read_bytes() == ref.tobytes()
+    r = subprocess.run([exe, "-i", str(x3a), "-o", str(wav_out)], capture_output=True, text=True)
+    assert r.returncode == 0 and "sample rate: 384000" in r.stdout, r.stderr
+    data = wav_out.read_bytes()
+    assert len(data) == 44 + 2 * pcm.size and np.array_equal(np.frombuffer(data[44:], dtype=np.int16), pcm)
+    # a damaged payload: samples before the bad frame are kept, the error is reported (decodefile.rs:97-100)
+    bad = bytearray(ref.tobytes()); bad[320 + 20 + 4000] ^= 0x40
+    (tmp_path / "bad.x3a").write_bytes(bytes(bad))
+    r = subprocess.run([exe, "-i", str(tmp_path / "bad.x3a"), "-o", str(tmp_path / "bad.wav")], capture_output=True, text=True)
+    assert r.returncode == 1 and "FrameHeaderInvalidPayloadCRC" in r.stderr
+    assert os.path.getsize(tmp_path / "bad.wav") == 44

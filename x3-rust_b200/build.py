@@ -29,7 +29,18 @@ def build(force=False, verbose=False):
     if verbose:
         cmd += ["-Xptxas", "-v"]
     subprocess.check_call(cmd)
+    build_cli()
     return SO
+
+
+def build_cli():
+    """x3-rust_b200/host/x3 : the reference's CLI (src/bin/x3.rs) over the C++ host mirror (host/x3.hpp)."""
+    host = os.path.join(HERE, "host")
+    exe = os.path.join(host, "x3")
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-o", exe, os.path.join(host, "x3_cli.cpp"),
+           "-L" + HERE, "-lx3b200", "-Wl,-rpath,$ORIGIN/.."]
+    subprocess.check_call(cmd)
+    return exe
 
 
 if __name__ == "__main__":

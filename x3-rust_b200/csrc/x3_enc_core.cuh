@@ -230,37 +230,56 @@ X3_HD BlockMode block_measure_fast(const int16_t *s, uint32_t start, uint32_t le
   return m;
 }
 
+// shared-memory word address: a 32-bit shared-window address on the device (so address selects are one
+// instruction), a plain pointer in the CPU simulation
+#if defined(__CUDA_ARCH__)
+typedef uint32_t smaddr_t;
+X3_HD smaddr_t sm_addr(const uint32_t *p) { return (smaddr_t)__cvta_generic_to_shared(p); }
+X3_HD void sm_store(smaddr_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+X3_HD void sm_store_if(bool pred, smaddr_t a, uint32_t v) {
+  asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.shared.u32 [%0], %1; }" ::"r"(a), "r"(v), "r"((uint32_t)pred) : "memory");
+}
+X3_HD smaddr_t sm_next(smaddr_t a) { return a + 4u; }
+#else
+typedef uint32_t *smaddr_t;
+X3_HD smaddr_t sm_addr(uint32_t *p) { return p; }
+X3_HD void sm_store(smaddr_t a, uint32_t v) { *a = v; }
+X3_HD void sm_store_if(bool pred, smaddr_t a, uint32_t v) { if (pred) *a = v; }
+X3_HD smaddr_t sm_next(smaddr_t a) { return a + 1; }
+#endif
+
 // MSB-first bit sink of the fast kernel.  A block whose first bit is not word aligned keeps its first word
 // out of the image (it goes to `first_slot`) and ORs it into place with one shared-memory atomic after all
 // plain stores are done; every other word -- including the zero-padded last partial word -- is a plain store
 // to its final position.  (The predecessor's last word, stored plainly, is the base the head is ORed into.)
+// flush() is branch free: a predicated store and three selects.
 struct FastSink {
   uint64_t acc;
   uint32_t cnt;
-  uint32_t *dst;
-  uint32_t *nxt;
+  smaddr_t dst;
+  smaddr_t nxt;
   X3_HD void init(uint32_t bit_off, uint32_t *out_words, uint32_t *first_slot) {
     acc = 0;
     cnt = bit_off & 31u;
     uint32_t *w = out_words + (bit_off >> 5);
-    dst = cnt ? first_slot : w;
-    nxt = w + 1;
+    dst = cnt ? sm_addr(first_slot) : sm_addr(w);
+    nxt = sm_addr(w + 1);
   }
   X3_HD void put(uint32_t v, uint32_t n) {  // v < 2^n, n <= 32, cnt + n <= 64
     acc = (acc << n) | (uint64_t)v;
     cnt += n;
   }
   X3_HD void flush() {
-    if (cnt >= 32u) {
-      cnt -= 32u;
-      *dst = bswap32((uint32_t)(acc >> cnt));
-      dst = nxt;
-      nxt = nxt + 1;
-    }
+    const bool f = cnt >= 32u;
+    const uint32_t nc = cnt - 32u;
+    sm_store_if(f, dst, bswap32((uint32_t)(acc >> (nc & 31u))));
+    dst = f ? nxt : dst;
+    nxt = f ? sm_next(nxt) : nxt;
+    cnt = f ? nc : cnt;
   }
   X3_HD void finish() {
     flush();
-    if (cnt) *dst = bswap32((uint32_t)(acc << (32u - cnt)));
+    if (cnt) sm_store(dst, bswap32((uint32_t)(acc << (32u - cnt))));
   }
 };
 

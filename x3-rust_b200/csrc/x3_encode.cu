@@ -343,23 +343,41 @@ __device__ __forceinline__ void bar_arrive_all(int id) {
 }
 constexpr int kBarSize = 2, kBarCrc = 5, kBarOff = 8;  // + buffer index (0..NB-1)
 
+// payload image (16-byte aligned in shared memory) -> dst (2-byte aligned global address), 512 worker threads.
+// Body in 16-byte stores; the shared-memory side is read at a 2- or 4-byte skew and realigned with PRMT.
 __device__ __forceinline__ void copy_payload_out(unsigned char *dst, const uint32_t *s_words, uint32_t L, int tid) {
-  // dst is 2-byte aligned; s_words is the 16-byte aligned payload image
-  const uintptr_t al = (uintptr_t)dst & 3u;
-  if (al == 0) {
-    uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
-    const uint32_t nw = L >> 2;
-    for (uint32_t i = tid; i < nw; i += 512) d32[i] = s_words[i];
-    if ((L & 2u) && tid == 0) *reinterpret_cast<uint16_t *>(dst + (nw << 2)) = (uint16_t)(s_words[nw] & 0xffffu);
-  } else if (al == 2) {
-    if (tid == 0) *reinterpret_cast<uint16_t *>(dst) = (uint16_t)(s_words[0] & 0xffffu);
-    uint32_t *d32 = reinterpret_cast<uint32_t *>(dst + 2);
-    const uint32_t nw = (L - 2u) >> 2;
-    for (uint32_t i = tid; i < nw; i += 512) d32[i] = __byte_perm(s_words[i], s_words[i + 1], 0x5432);
-    if (((L - 2u) & 2u) && tid == 0) *reinterpret_cast<uint16_t *>(dst + 2 + (nw << 2)) = (uint16_t)(s_words[nw] >> 16);
-  } else {
+  if (((uintptr_t)dst & 1u) != 0) {  // odd output base: bytewise
     const unsigned char *sb = reinterpret_cast<const unsigned char *>(s_words);
     for (uint32_t i = tid; i < L; i += 512) dst[i] = sb[i];
+    return;
+  }
+  uint32_t head = (uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u);  // bytes until dst is 16-byte aligned (even)
+  if (head > L) head = L;
+  const uint32_t nvec = (L - head) >> 4;
+  const uint32_t tail0 = head + (nvec << 4);
+  const uint16_t *s16 = reinterpret_cast<const uint16_t *>(s_words);
+  // head and tail halfwords (at most 7 + 7)
+  if ((uint32_t)tid < (head >> 1)) reinterpret_cast<uint16_t *>(dst)[tid] = s16[tid];
+  if ((uint32_t)tid >= 32u && (uint32_t)tid - 32u < ((L - tail0) >> 1))
+    reinterpret_cast<uint16_t *>(dst + tail0)[tid - 32] = s16[(tail0 >> 1) + (tid - 32)];
+  uint4 *d4 = reinterpret_cast<uint4 *>(dst + head);
+  const uint32_t w0 = head >> 2;          // first source word
+  if ((head & 3u) == 0u) {
+    for (uint32_t i = tid; i < nvec; i += 512) {
+      const uint32_t *q = s_words + w0 + 4u * i;
+      uint4 v;
+      v.x = q[0]; v.y = q[1]; v.z = q[2]; v.w = q[3];
+      d4[i] = v;
+    }
+  } else {                                // source starts in the middle of a word
+    for (uint32_t i = tid; i < nvec; i += 512) {
+      const uint32_t *q = s_words + w0 + 4u * i;
+      const uint32_t a0 = q[0], a1 = q[1], a2 = q[2], a3 = q[3], a4 = q[4];
+      uint4 v;
+      v.x = __byte_perm(a0, a1, 0x5432); v.y = __byte_perm(a1, a2, 0x5432);
+      v.z = __byte_perm(a2, a3, 0x5432); v.w = __byte_perm(a3, a4, 0x5432);
+      d4[i] = v;
+    }
   }
 }
 
@@ -374,6 +392,7 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
   uint16_t *s_crcT = reinterpret_cast<uint16_t *>(p);             p += kCrcTableEntries * 2;
   uint32_t *s_first = reinterpret_cast<uint32_t *>(p);            p += 512 * 4;
   uint32_t *s_V = reinterpret_cast<uint32_t *>(p);                p += NB * kMaxSlices * 4;
+  unsigned char *s_stat = p;                                       p += NB * 512;  // per block: stats index, 7 = none
   uint32_t *s_misc = reinterpret_cast<uint32_t *>(p);
   // s_misc: [0..16) warp totals, [32] next ticket, [40..46) stats of short blocks,
   //         per parity q at [48+8q ..): +0 frame, +1 samples, +2 payload_len, +4,+5 byte offset, +6 fits
@@ -392,6 +411,7 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
 
   if (!worker) {
     // ================================ control warp ================================
+    uint32_t mode_blocks[6] = {0u, 0u, 0u, 0u, 0u, 0u};
     for (uint32_t par = 0;; par = (par + 1u == NB ? 0u : par + 1u)) {
       uint32_t *info = s_misc + 48 + 8 * par;
       bar_sync_all(kBarSize + par);
@@ -399,6 +419,22 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
       if (f == kNoFrame) break;
       const uint32_t n = info[1], payload_len = info[2];
       const uint32_t frame_bytes = (uint32_t)kFrameHeaderLen + payload_len;
+      {
+        // histogram of the 512 per-block stats bytes: each lane counts its 16 bytes per mode (exact zero-byte test)
+        const uint4 sq = reinterpret_cast<const uint4 *>(s_stat + par * 512)[lane];
+        const uint32_t w4[4] = {sq.x, sq.y, sq.z, sq.w};
+#pragma unroll
+        for (int m = 0; m < 6; m++) {
+          uint32_t c = 0;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const uint32_t x = w4[k] ^ (0x01010101u * (uint32_t)m);
+            const uint32_t t = ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu);  // 0x80 in every zero byte
+            c += __popc(t);
+          }
+          mode_blocks[m] += c;
+        }
+      }
       const unsigned long long excl = lookback_exclusive(a.status, f, frame_bytes);
       const bool fits = excl + frame_bytes <= a.out_cap;
       if (lane == 0) {
@@ -440,13 +476,19 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
       __syncwarp();
       bar_arrive_all(kBarOff + par);
     }
+#pragma unroll
+    for (int m = 0; m < 6; m++) {
+      uint32_t c = mode_blocks[m];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+      if (lane == 0 && c) atomicAdd(a.result + 2 + m, (unsigned long long)c * BL);
+    }
     return;
   }
 
   // ================================== workers ==================================
   uint32_t f = blockIdx.x;
   if (f < a.n_frames) issue_frame_load<512>(a, f, s_in);
-  uint32_t full_block_count = 0;
   uint32_t it = 0, par = 0;
   uint32_t hist_len[NB];  // payload lengths of the frames still held in the image ring
 #pragma unroll
@@ -482,15 +524,10 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
       }
       if (b == 0) nbits += 16;  // <Audio State>, encoder.rs:189
     }
-    {
-      const bool full = active && len == BL;
-#pragma unroll
-      for (int m = 0; m < 6; m++) {
-        const unsigned bal = __ballot_sync(0xffffffffu, full && mode.stat == (uint32_t)m);
-        if (lane == m) full_block_count += __popc(bal);
-      }
-      if (active && len != BL && len > 0) atomicAdd(&s_misc[40 + mode.stat], len);
-    }
+    // statistics (stats[ftype] += block.len(), encoder.rs:199): full blocks leave one byte for the control
+    // warp to histogram; the rare short block adds its length directly
+    s_stat[par * 512 + tid] = (unsigned char)((active && len == BL) ? mode.stat : 7u);
+    if (active && len != BL && len > 0) atomicAdd(&s_misc[40 + mode.stat], len);
     uint32_t incl = nbits;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -609,7 +646,6 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
     if (tid == 0) s_misc[48 + 8 * par] = kNoFrame;
     bar_arrive_all(kBarSize + par);
   }
-  if (lane < 6 && full_block_count) atomicAdd(a.result + 2 + lane, (unsigned long long)full_block_count * BL);
   bar_workers();
   if (tid < 6 && s_misc[40 + tid]) atomicAdd(a.result + 2 + tid, (unsigned long long)s_misc[40 + tid]);
 }
@@ -628,7 +664,7 @@ size_t encode_smem_bytes(const CodecParams &P, uint32_t max_blocks, uint32_t out
 size_t encode_fast_smem_bytes(const CodecParams &P, uint32_t out_words_cap) {
   const uint32_t in_bytes = (2u * (P.spf + 8u) + 15u) & ~15u;
   const uint32_t img_bytes = (4u * (out_words_cap + 8u) + 15u) & ~15u;
-  return (size_t)in_bytes + NB * img_bytes + kCrcTableEntries * 2 + 512u * 4u + NB * kMaxSlices * 4u + 96u * 4u;
+  return (size_t)in_bytes + NB * img_bytes + kCrcTableEntries * 2 + 512u * 4u + NB * kMaxSlices * 4u + NB * 512u + 96u * 4u;
 }
 
 cudaError_t launch_encode(const EncodeArgs &a, bool fast, int grid, size_t smem, cudaStream_t stream) {

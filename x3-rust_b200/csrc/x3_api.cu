@@ -307,9 +307,20 @@ int x3_encode_device(const int16_t *d_pcm, size_t n_samples, const x3_params *p,
   a.status = reinterpret_cast<unsigned long long *>(ws + 128);
   a.crc_tables = ds->crc_dev;
 
+  // the fast kernel stages frames with 16-byte cp.async: it needs a 16-byte aligned base and frame size
+  if (d.fast && ((((uintptr_t)d_pcm) & 15u) != 0 || ((d.P.spf * 2u) & 15u) != 0)) {
+    d.fast = false;
+    d.smem = encode_smem_bytes(d.P, d.max_blocks, d.out_words_cap);
+    if (d.smem > kMaxDynSmem) return X3_ERR_UNSUPPORTED_PARAMS;
+  }
   const int occ = encode_occupancy(d.fast, d.smem);
   unsigned long long grid = (unsigned long long)ds->sms * (unsigned)occ;
-  if (grid > nf) grid = nf;
+  if (d.fast) {  // CTA 0 is the scanner, the others encode
+    if (grid > nf + 1) grid = nf + 1;
+    if (grid < 2) grid = 2;
+  } else if (grid > nf) {
+    grid = nf;
+  }
   Timer tm(st);
   tm.start();
   e = launch_encode(a, d.fast, (int)grid, d.smem, st);

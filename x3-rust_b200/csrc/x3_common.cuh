@@ -68,8 +68,36 @@ X3_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {
   return (lo >> s) | (hi << (32 - s));
 #endif
 }
-X3_HD uint32_t shl_safe(uint32_t v, uint32_t s) { return s >= 32 ? 0u : v << s; }
-X3_HD uint32_t shr_safe(uint32_t v, uint32_t s) { return s >= 32 ? 0u : v >> s; }
+// shifts that are defined for any amount: PTX shl/shr clamp the amount to 32 (one SHF), C++ needs the select
+X3_HD uint32_t shl_safe(uint32_t v, uint32_t s) {
+#if defined(__CUDA_ARCH__)
+  uint32_t r;
+  asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(s));
+  return r;
+#else
+  return s >= 32 ? 0u : v << s;
+#endif
+}
+X3_HD uint32_t shr_safe(uint32_t v, uint32_t s) {
+#if defined(__CUDA_ARCH__)
+  uint32_t r;
+  asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(s));
+  return r;
+#else
+  return s >= 32 ? 0u : v >> s;
+#endif
+}
+// leading zeros as a shift amount: clz for x != 0; for x == 0 the device returns 0xffffffff (bfind.shiftamt, one
+// FLO) and the host 32 -- callers only rely on "x == 0 gives a value >= 32"
+X3_HD uint32_t clz_shift(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  uint32_t r;
+  asm("bfind.shiftamt.u32 %0, %1;" : "=r"(r) : "r"(x));
+  return r;
+#else
+  return x ? (uint32_t)__builtin_clz(x) : 32u;
+#endif
+}
 
 // zig-zag fold of the first difference: u = d<0 ? -2d-1 : 2d  (closed form of the `offset` indexing of
 // x3.rs:207-252, verified against the four tables by tests/test_oracle_golden.py)

@@ -250,16 +250,21 @@ X3_HD bool frame_fast_eligible(uint32_t samples, uint32_t payload_len, uintptr_t
          (payload_addr & 1u) == 0u && (out_addr & 31u) == 0u;
 }
 
-// one Rice code at offset `cum` of the window (decoder.rs:157-165 / :184-191 in closed form)
+// one Rice code at offset `cum` of the window (decoder.rs:157-165 / :184-191 in closed form):
+//   z zeros, then nbk bits r of which the first is the terminator; index i = r + level*(z-1); delta = INV[i].
+// ip = i + level is what is tracked (one IMAD); delta = (i>>1) - (i odd ? i : 0).
+// An all-zero window gives z >= 32 (0xffffffff on the device): ip is then far beyond every inv_len.
 #define X3_RICE_SAMPLE()                                                              \
   {                                                                                   \
     const uint32_t t = bw.peek(cum);                                                  \
-    const uint32_t z = clz32(t);                                                      \
+    const uint32_t z = clz_shift(t);                                                  \
     const uint32_t r = shl_safe(t, z) >> (32u - nbk);                                 \
     cum += z + nbk;                                                                   \
-    const uint32_t i = (uint32_t)((int32_t)r + level * ((int32_t)z - 1));             \
-    max_i = i > max_i ? i : max_i;                                                    \
-    lw += unfold(i);                                                                  \
+    const uint32_t ip = z * (uint32_t)level + r;                                      \
+    max_ip = ip > max_ip ? ip : max_ip;                                               \
+    const uint32_t i = ip - (uint32_t)level;                                          \
+    lw += (int32_t)(i >> 1);                                                          \
+    if (i & 1u) lw -= (int32_t)i;                                                     \
   }
 
 // Decode one frame.  `stage` = this thread's 44-word staging area (16-byte aligned).
@@ -292,7 +297,7 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
       const uint32_t nbk = ftype == 1u ? 1u : (ftype == 2u ? 2u : 4u);          // decoder.rs:158,180
       const int32_t level = ftype == 1u ? 1 : (ftype == 2u ? 2 : 8);            // 1<<nsubs of RICE1 / RICE3
       const uint32_t inv_len = ftype == 1u ? 16u : (ftype == 2u ? 26u : 60u);   // x3.rs:214,222,250
-      uint32_t max_i = 0, cum = 0, cmax = 0;
+      uint32_t max_ip = 0, cum = 0, cmax = 0;
       // samples x0..x19; output words (prev,x0) (x1,x2) ... (x17,x18); x19 becomes prev.
       // A valid code is at most 10 bits, so three codes are parsed per refill / consume.
 #pragma unroll
@@ -310,7 +315,7 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
       }
       // out-of-range index (decoder.rs:161,187; includes every zero run the 32-bit peek cannot see the end of)
       // or a group of codes longer than the 32 valid bits a refill guarantees -> let the exact path decide
-      if (max_i >= inv_len || cmax > 32u) bad = true;
+      if (max_ip >= inv_len + (uint32_t)level || cmax > 32u) bad = true;
     } else {
       const uint32_t nb = ((hdr >> 26) & 15u) + 1u;  // decoder.rs:211
       bw.consume(6);

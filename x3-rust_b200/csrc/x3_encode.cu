@@ -312,6 +312,24 @@ constexpr int kMaxSlices = 64;
 constexpr uint32_t kNoFrame = 0xffffffffu;
 constexpr uint32_t NB = 3;                // frame images in flight per CTA (slack for the look-back: NB-1 frames)
 
+// lean frame stager for the fast kernel: the API guarantees a 16-byte aligned PCM base and frame size there, so
+// it is two or three cp.async per worker thread with 32-bit index math (the generic stager costs ~100
+// instructions per thread and frame)
+__device__ __forceinline__ void stage_frame_fast(const int16_t *pcm, unsigned long long s0, uint32_t n, int16_t *s_in, int tid) {
+  const char *g = reinterpret_cast<const char *>(pcm + s0) + tid * 16;
+  uint32_t sa = (uint32_t)__cvta_generic_to_shared(s_in) + (uint32_t)tid * 16u;
+  const uint32_t chunks = n >> 3;  // 8 samples = 16 bytes
+  for (uint32_t c = tid; c < chunks; c += 512u) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(g) : "memory");
+    sa += 512u * 16u;
+    g += 512 * 16;
+  }
+  if (n & 7u) {  // only the stream's last frame
+    for (uint32_t i = (chunks << 3) + tid; i < n; i += 512u) s_in[i] = __ldg(pcm + s0 + i);
+  }
+  cp_async_commit();
+}
+
 __device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 1, 512;\n" ::: "memory"); }
 // barrier ids are immediates so that ptxas reserves exactly the eight barriers used (not all sixteen)
 __device__ __forceinline__ void bar_sync_all(int id) {
@@ -381,7 +399,63 @@ __device__ __forceinline__ void copy_payload_out(unsigned char *dst, const uint3
   }
 }
 
+// Scanner role (CTA 0, one warp): turns the frame sizes the workers publish (kFlagAgg | bytes) into inclusive
+// prefixes (kFlagPrefix | bytes through this frame), in order, up to 256 frames per round trip.  Every frame's
+// control warp then polls only its own status word.  (With a per-frame decoupled look-back every one of the
+// ~300 resident CTAs walks the same few hundred entries again and again; one scanner does that work once.)
+__device__ __forceinline__ void scanner_role(const EncodeArgs &a) {
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  constexpr int G = 8;
+  unsigned long long frontier = 0, running = 0;
+  const unsigned long long nf = a.n_frames;
+  while (frontier < nf) {
+    unsigned long long v[G];
+    const unsigned long long base_idx = frontier + (unsigned long long)(G * lane);
+#pragma unroll
+    for (int g = 0; g < G; g++) v[g] = base_idx + g < nf ? ld_status(a.status + base_idx + g) : 0ull;
+    int ready = 0;  // leading published entries of this lane
+    unsigned long long incl[G], run = 0;
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      if (ready == g && (v[g] >> 62) != 0ull) ready = g + 1;
+      run += v[g] & kValueMask;
+      incl[g] = run;
+    }
+    const unsigned notfull = __ballot_sync(0xffffffffu, ready < G);
+    const int L = notfull ? __ffs((int)notfull) - 1 : 32;   // first lane that is not completely ready
+    if (lane > L) ready = 0;
+    const int total_ready = __reduce_add_sync(0xffffffffu, ready);
+    if (total_ready == 0) { __nanosleep(100); continue; }
+    unsigned long long t = ready ? incl[ready - 1 < G ? ready - 1 : G - 1] : 0ull;
+    {
+      // pick incl[ready-1] without dynamic register indexing
+      unsigned long long pick = 0;
+#pragma unroll
+      for (int g = 0; g < G; g++) if (ready == g + 1) pick = incl[g];
+      t = pick;
+    }
+    unsigned long long scan = t;  // inclusive scan of lane totals
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long o = __shfl_up_sync(0xffffffffu, scan, d);
+      if (lane >= d) scan += o;
+    }
+    const unsigned long long lane_base = running + scan - t;
+#pragma unroll
+    for (int g = 0; g < G; g++)
+      if (g < ready) st_status(a.status + base_idx + g, kFlagPrefix | ((lane_base + incl[g]) & kValueMask));
+    running += __shfl_sync(0xffffffffu, scan, 31);
+    frontier += (unsigned long long)total_ready;
+  }
+  if (lane == 0) a.result[0] = running;  // total stream length
+}
+
 __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const EncodeArgs a) {
+  if (blockIdx.x == 0) {
+    scanner_role(a);
+    return;
+  }
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t in_bytes = (2u * (a.P.spf + 8u) + 15u) & ~15u;
   const uint32_t img_bytes = (4u * (a.out_words_cap + 8u) + 15u) & ~15u;
@@ -404,10 +478,10 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
   for (int i = tid; i < kCrcTableEntries; i += NTF) s_crcT[i] = a.crc_tables[i];
   if (tid < 6) s_misc[40 + tid] = 0;
   __syncthreads();
-  // Frames are dealt round-robin: CTA c takes frames c, c+G, c+2G, ...  (the grid is sized so that every CTA
-  // is resident).  A frame's predecessors are then being worked on at the same time as the frame itself, which
-  // keeps the look-back short; handing frames out early through an atomic ticket (to prefetch them) leaves
-  // ticketed-but-unmeasured predecessors in the window for a whole frame time.
+  // Frames are handed out by an atomic ticket, LATE: a CTA draws its next frame only when it has finished packing
+  // the current one, so that a ticketed frame publishes its size within about one measure phase.  (Drawing the
+  // ticket a whole frame early -- to prefetch -- leaves unmeasured predecessors in everybody's look-back window
+  // for a frame time; dealing frames round-robin makes every frame wait for the slowest CTA of its round.)
 
   if (!worker) {
     // ================================ control warp ================================
@@ -435,12 +509,15 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
           mode_blocks[m] += c;
         }
       }
-      const unsigned long long excl = lookback_exclusive(a.status, f, frame_bytes);
-      const bool fits = excl + frame_bytes <= a.out_cap;
+      // this frame's byte offset: wait for the scanner to turn the published size into a prefix
+      unsigned long long pv = 0;
       if (lane == 0) {
-        if (!fits) atomicMax(a.result + 1, 1ull);                    // ByteWriterInsufficientMemory, bytewriter.rs:88
-        if (f == a.n_frames - 1) a.result[0] = excl + frame_bytes;   // total stream length
+        while (((pv = ld_status(a.status + f)) >> 62) != 2ull) __nanosleep(64);
       }
+      pv = __shfl_sync(0xffffffffu, pv, 0);
+      const unsigned long long excl = (pv & kValueMask) - frame_bytes;
+      const bool fits = excl + frame_bytes <= a.out_cap;
+      if (lane == 0 && !fits) atomicMax(a.result + 1, 1ull);         // ByteWriterInsufficientMemory, bytewriter.rs:88
       bar_sync_all(kBarCrc + par);
       // payload CRC = sum_j V_j * x^(4096 j), then the tail bytes, then the header
       const uint32_t *s_words = s_img + par * img_words;
@@ -487,14 +564,20 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
   }
 
   // ================================== workers ==================================
-  uint32_t f = blockIdx.x;
-  if (f < a.n_frames) issue_frame_load<512>(a, f, s_in);
+  if (tid == 0) s_misc[32] = atomicAdd(a.ticket, 1u);
+  bar_workers();
+  uint32_t f = s_misc[32];
+  if (f < a.n_frames) {
+    const unsigned long long s00 = (unsigned long long)f * a.P.spf;
+    const unsigned long long r0 = a.n_samples - s00;
+    stage_frame_fast(a.pcm, s00, r0 < a.P.spf ? (uint32_t)r0 : a.P.spf, s_in, tid);
+  }
   uint32_t it = 0, par = 0;
   uint32_t hist_len[NB];  // payload lengths of the frames still held in the image ring
 #pragma unroll
   for (uint32_t q = 0; q < NB; q++) hist_len[q] = 0;
 
-  while (f < a.n_frames) {
+  while (f != kNoFrame && f < a.n_frames) {
     uint32_t *s_words = s_img + par * img_words;
     const unsigned long long s0 = (unsigned long long)f * a.P.spf;
     const unsigned long long remn = a.n_samples - s0;
@@ -546,19 +629,17 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
     }
     const uint32_t total_bits = __shfl_sync(0xffffffffu, wincl, NWW - 1);
     const uint32_t payload_len = payload_bytes(total_bits);
-    const uint32_t f_next = f + gridDim.x < a.n_frames ? f + gridDim.x : kNoFrame;
     if (tid == 0) {
       uint32_t *info = s_misc + 48 + 8 * par;
       info[0] = f; info[1] = n; info[2] = payload_len;
       // publish the frame size right away (the control warp may still be busy with the previous frame)
-      st_status(a.status + f, (f == 0 ? kFlagPrefix : kFlagAgg) | (unsigned long long)(kFrameHeaderLen + payload_len));
+      st_status(a.status + f, kFlagAgg | (unsigned long long)(kFrameHeaderLen + payload_len));
     }
     bar_arrive_all(kBarSize + par);  // -> control: frame size known
 
     // ---- prefetch the next frame, pack this one ----
     const uint32_t warp_base = __shfl_sync(0xffffffffu, wincl - wt, wid);
     const uint32_t bit_off = warp_base + (incl - nbits);
-    if (f_next < a.n_frames) issue_frame_load<512>(a, f_next, s_in);
     if (active) {
       FastSink sink;
       sink.init(bit_off, s_words, &s_first[tid]);
@@ -573,9 +654,19 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
         sink.finish();
       }
     }
+    if (tid == 0) s_misc[32] = atomicAdd(a.ticket, 1u);  // this CTA's next frame
     bar_workers();  // (D) every plain store done
+    uint32_t f_next = s_misc[32];
+    if (f_next >= a.n_frames) f_next = kNoFrame;
     if (active && (bit_off & 31u)) atomicOr(&s_words[bit_off >> 5], s_first[tid]);
     bar_workers();  // (E) payload image complete
+    // stage the next frame now: s_in has been free since barrier (B), and the copy lands while the CRC and
+    // the copy-out run
+    if (f_next != kNoFrame) {
+      const unsigned long long s1 = (unsigned long long)f_next * a.P.spf;
+      const unsigned long long r1 = a.n_samples - s1;
+      stage_frame_fast(a.pcm, s1, r1 < a.P.spf ? (uint32_t)r1 : a.P.spf, s_in, tid);
+    }
 
     // ---- CRC of 16-byte chunks, combined per slice of 32 chunks by a shuffle tree.  Slice j covers the
     // chunks at distance 32j .. 32j+31 from the end; V_j = sum_l x^(128 l) * crc(chunk at distance 32j+l). ----

@@ -36,6 +36,16 @@ METRIC = "round-trip (encode + decode) throughput"
 UNIT = "Msamples/s"
 
 
+def measured_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the main kernels from the committed
+    `ncu --set full` capture of this workload (profiles/r01_traffic.json); None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -311,8 +321,11 @@ def main():
         "decode_all_kernels_ms": dec_ms + crc_ms + idx_ms,
     }
     dom = "decode_frames_kernel" if dec_ms >= enc_ms else "encode_frames_kernel"
+    traffic = measured_traffic() if (world == 1 and n == N_C2) else {}
+    for k in ("encode_frames_kernel", "decode_frames_kernel"):
+        kernels[k]["traffic_bytes_ncu"] = traffic.get(k)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "frac": kernels[dom]["frac"], "traffic": traffic.get(dom), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "note": "2 B/sample PCM + compressed frame bytes, per launch over the whole batch"}
 

@@ -269,7 +269,7 @@ int sim_decode_frame(const uint8_t *stream, size_t stream_len, size_t pos, uint3
   if (samples == 0 || payload_len < 2) return kDecErrPanic;
   if (mode == 0 && dflt && frame_fast_eligible(samples, payload_len, (uintptr_t)pl, (uintptr_t)out)) {
     alignas(16) uint32_t stage[kStageWords];
-    PlainWordReader rd;
+    PlainBitReader rd;
     rd.init(pl, stream + stream_len);
     r = decode_frame_fast(rd, payload_len, out, samples, stage);
     if (r == kDecOk) *used_fast = 1;

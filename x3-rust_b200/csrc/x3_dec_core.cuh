@@ -176,69 +176,32 @@ X3_HD uint32_t crc16_bytes(const uint16_t *T, const uint8_t *d, uint32_t n) {
 // Fast path
 // ------------------------------------------------------------------------------------------------
 
-// Reader concept: uint32_t next() returns the next 32 payload bits (big-endian numeric, first stream byte
-// in bits 31..24).  It may return bytes that lie after the payload; decode_frame_fast checks at the end
-// that it never consumed a bit past the payload (the reference zero-fills there) and retries exactly if so.
+// Reader concept (fast path): the payload is addressed by BIT POSITION, there is no bit-buffer state:
+//   uint32_t start_pos()                 bit position of the payload's first bit
+//   void block_begin(uint32_t pos)       called once per block (the device reader tops up its ring here)
+//   void fetch(pos, hi, lo)              the 64 bits that start at bit `pos` (big-endian numeric)
+// fetch may return bytes that lie after the payload; decode_frame_fast checks at the end that it never consumed
+// a bit past the payload (the reference zero-fills there) and retries exactly if so.
 
-// Plain reader over memory through aligned 32-bit loads (host simulation and the device fallback).
-struct PlainWordReader {
-  const uint32_t *base;   // aligned word containing the payload's first byte
-  uint32_t k;             // next aligned word to load
-  uint32_t carry;         // previous loaded word (big-endian), for the 2-byte misaligned case
-  uint32_t sh;            // 32 when aligned, 16 when the payload starts in the middle of a word
-  uint32_t n_load;        // aligned words that may be loaded whole (all inside the stream buffer)
-  const uint8_t *end;     // end of the stream buffer
-
-  X3_HD uint32_t load(uint32_t i) const {
-    if (i < n_load) return bswap32(base[i]);
-    const uint8_t *p = reinterpret_cast<const uint8_t *>(base + i);  // word straddles / lies past the end
-    uint32_t w = 0;
-    for (int b = 0; b < 4; b++) w = (w << 8) | ((p + b < end) ? (uint32_t)p[b] : 0u);
-    return w;
-  }
-  X3_HD void init(const uint8_t *payload, const uint8_t *stream_end) {
-    end = stream_end;
-    const uintptr_t addr = (uintptr_t)payload;
-    base = reinterpret_cast<const uint32_t *>(addr & ~(uintptr_t)3);
-    const uintptr_t lim = (uintptr_t)stream_end & ~(uintptr_t)3;
-    n_load = lim > (uintptr_t)base ? (uint32_t)((lim - (uintptr_t)base) >> 2) : 0u;
-    if (addr & 2u) { sh = 16; carry = load(0); k = 1; }
-    else { sh = 32; carry = 0; k = 0; }
-  }
-  X3_HD void block_begin() {}
-  X3_HD uint32_t next() {
-    const uint32_t w = load(k);
-    k++;
-    const uint32_t v = funnel_l(w, carry, sh);
-    carry = w;
-    return v;
-  }
-};
-
-#if defined(__CUDA_ARCH__)
-#define X3_SHL64(v, s) ((v) << (s))
-#else
-#define X3_SHL64(v, s) ((s) >= 64 ? 0ull : ((v) << (s)))
-#endif
-
-struct BitWindow {
-  uint64_t bb;      // left-aligned bit buffer
-  int cnt;          // valid bits in bb
-  uint32_t words;   // words pulled from the reader
-  template <class Reader>
-  X3_HD void refill(Reader &rd) {
-    if (cnt <= 32) {
-      const uint32_t w = rd.next();
-      bb |= X3_SHL64((uint64_t)w, (unsigned)(32 - cnt));
-      cnt += 32;
-      words++;
+// Plain reader over memory (host simulation): assembles the window bytewise, zero past the buffer end.
+struct PlainBitReader {
+  const uint8_t *payload;
+  const uint8_t *end;
+  X3_HD void init(const uint8_t *p, const uint8_t *stream_end) { payload = p; end = stream_end; }
+  X3_HD uint32_t start_pos() const { return 0u; }
+  X3_HD void block_begin(uint32_t) {}
+  X3_HD void fetch(uint32_t pos, uint32_t &hi, uint32_t &lo) const {
+    const uint8_t *p = payload + (pos >> 3);
+    uint32_t w[3];
+    for (int k = 0; k < 3; k++) {
+      uint32_t v = 0;
+      for (int b = 0; b < 4; b++) v = (v << 8) | ((p + 4 * k + b < end) ? (uint32_t)p[4 * k + b] : 0u);
+      w[k] = v;
     }
+    const uint32_t s = pos & 7u;
+    hi = funnel_l(w[1], w[0], s);
+    lo = funnel_l(w[2], w[1], s);
   }
-  X3_HD uint32_t hi() const { return (uint32_t)(bb >> 32); }
-  X3_HD uint32_t lo() const { return (uint32_t)bb; }
-  // the 32 bits that start s bits into the window (s <= 32)
-  X3_HD uint32_t peek(uint32_t s) const { return funnel_l(lo(), hi(), s); }
-  X3_HD void consume(uint32_t n) { bb = X3_SHL64(bb, n); cnt -= (int)n; }
 };
 
 constexpr uint32_t kFastGroup = 80;        // samples per staged flush (4 blocks of 20)
@@ -250,13 +213,13 @@ X3_HD bool frame_fast_eligible(uint32_t samples, uint32_t payload_len, uintptr_t
          (payload_addr & 1u) == 0u && (out_addr & 31u) == 0u;
 }
 
-// one Rice code at offset `cum` of the window (decoder.rs:157-165 / :184-191 in closed form):
+// one Rice code at offset `cum` of the 64-bit window (decoder.rs:157-165 / :184-191 in closed form):
 //   z zeros, then nbk bits r of which the first is the terminator; index i = r + level*(z-1); delta = INV[i].
 // ip = i + level is what is tracked (one IMAD); delta = (i>>1) - (i odd ? i : 0).
 // An all-zero window gives z >= 32 (0xffffffff on the device): ip is then far beyond every inv_len.
 #define X3_RICE_SAMPLE()                                                              \
   {                                                                                   \
-    const uint32_t t = bw.peek(cum);                                                  \
+    const uint32_t t = funnel_l(lo, hi, cum);                                         \
     const uint32_t z = clz_shift(t);                                                  \
     const uint32_t r = shl_safe(t, z) >> (32u - nbk);                                 \
     cum += z + nbk;                                                                   \
@@ -271,12 +234,13 @@ X3_HD bool frame_fast_eligible(uint32_t samples, uint32_t payload_len, uintptr_t
 // Returns kDecOk or kDecRetryExact.
 template <class Reader>
 X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint32_t samples, uint32_t *stage) {
-  BitWindow bw;
-  bw.bb = 0; bw.cnt = 0; bw.words = 0;
-  rd.block_begin();
-  bw.refill(rd);
-  int32_t lw = (int32_t)(bw.hi() >> 16);   // first sample, decoder.rs:42 (only the low 16 bits of lw matter)
-  bw.consume(16);
+  const uint32_t pos0 = rd.start_pos();
+  uint32_t pos = pos0;
+  uint32_t hi, lo;
+  rd.block_begin(pos);
+  rd.fetch(pos, hi, lo);
+  int32_t lw = (int32_t)(hi >> 16);        // first sample, decoder.rs:42 (only the low 16 bits of lw matter)
+  pos += 16;
   uint32_t prev = (uint32_t)lw;            // last sample not yet written (low half of the next output word)
   bool bad = false;
 
@@ -284,25 +248,24 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
   uint4 *out4 = reinterpret_cast<uint4 *>(out);
 
   for (uint32_t b = 0; b < nblk; b++) {
-    if (b) rd.block_begin();
+    rd.block_begin(pos);
     const bool tail = (b == nblk - 1u);
     uint32_t *st = stage + (b & 3u) * 10u;
 
-    bw.refill(rd);
-    const uint32_t hdr = bw.hi();
-    const uint32_t ftype = hdr >> 30;
+    rd.fetch(pos, hi, lo);
+    const uint32_t ftype = hi >> 30;
     if (ftype != 0u) {
       // ---- Rice block: z zeros, then nbk bits of which the first is the terminator ----
-      bw.consume(2);
+      pos += 2;
       const uint32_t nbk = ftype == 1u ? 1u : (ftype == 2u ? 2u : 4u);          // decoder.rs:158,180
       const int32_t level = ftype == 1u ? 1 : (ftype == 2u ? 2 : 8);            // 1<<nsubs of RICE1 / RICE3
       const uint32_t inv_len = ftype == 1u ? 16u : (ftype == 2u ? 26u : 60u);   // x3.rs:214,222,250
       uint32_t max_ip = 0, cum = 0, cmax = 0;
       // samples x0..x19; output words (prev,x0) (x1,x2) ... (x17,x18); x19 becomes prev.
-      // A valid code is at most 10 bits, so three codes are parsed per refill / consume.
+      // A valid code is at most 10 bits, so three codes are parsed per 64-bit window.
 #pragma unroll
       for (int i = 0; i < 20; i++) {
-        if (i % 3 == 0) { bw.refill(rd); cum = 0; }
+        if (i % 3 == 0) { rd.fetch(pos, hi, lo); cum = 0; }
         if (i < 19 || !tail) {
           X3_RICE_SAMPLE();
           if ((i & 1) == 0) st[i >> 1] = (prev & 0xffffu) | ((uint32_t)lw << 16);
@@ -310,47 +273,48 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
         }
         if (i % 3 == 2 || i == 19) {
           cmax = cum > cmax ? cum : cmax;
-          bw.consume(cum);
+          pos += cum;
         }
       }
       // out-of-range index (decoder.rs:161,187; includes every zero run the 32-bit peek cannot see the end of)
-      // or a group of codes longer than the 32 valid bits a refill guarantees -> let the exact path decide
+      // or a group of codes longer than 32 bits (its later codes were parsed from the wrong place) -> the exact
+      // path decides
       if (max_ip >= inv_len + (uint32_t)level || cmax > 32u) bad = true;
     } else {
-      const uint32_t nb = ((hdr >> 26) & 15u) + 1u;  // decoder.rs:211
-      bw.consume(6);
+      const uint32_t nb = ((hi >> 26) & 15u) + 1u;  // decoder.rs:211
+      pos += 6;
       if (nb <= 5u) { bad = true; break; }           // FrameDecodeInvalidBPF, decoder.rs:213-216
       if (nb == 16u) {
         // ---- literal block: raw 16-bit samples ----
         for (int j = 0; j < 10; j++) {
-          bw.refill(rd);
-          lw = (int32_t)(bw.hi() >> 16);
+          rd.fetch(pos, hi, lo);
+          lw = (int32_t)(hi >> 16);
           st[j] = (prev & 0xffffu) | ((uint32_t)lw << 16);
           if (j < 9 || !tail) {
-            lw = (int32_t)(bw.hi() & 0xffffu);
+            lw = (int32_t)(hi & 0xffffu);
             prev = (uint32_t)lw;
-            bw.consume(32);
+            pos += 32;
           } else {
-            bw.consume(16);
+            pos += 16;
           }
         }
       } else {
         // ---- BFP block: nb-bit two's complement differences (decoder.rs:224-231) ----
         const int32_t half = 1 << (nb - 1u), full = 1 << nb;
         for (int j = 0; j < 10; j++) {
-          bw.refill(rd);
-          int32_t v = (int32_t)(bw.hi() >> (32u - nb));
+          rd.fetch(pos, hi, lo);
+          int32_t v = (int32_t)(hi >> (32u - nb));
           if (v > half) v -= full;                    // unsigned_to_i16: strictly greater, decoder.rs:203
           lw += v;
           st[j] = (prev & 0xffffu) | ((uint32_t)lw << 16);
           if (j < 9 || !tail) {
-            v = (int32_t)(bw.peek(nb) >> (32u - nb));
+            v = (int32_t)(funnel_l(lo, hi, nb) >> (32u - nb));
             if (v > half) v -= full;
             lw += v;
             prev = (uint32_t)lw;
-            bw.consume(2u * nb);
+            pos += 2u * nb;
           } else {
-            bw.consume(nb);
+            pos += nb;
           }
         }
       }
@@ -367,8 +331,7 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
   if (bad) return kDecRetryExact;
   // bits consumed must lie inside the payload (the reference zero-fills past the end; we may have read
   // the next frame's bytes there instead)
-  const long long used = 32ll * (long long)bw.words - (long long)bw.cnt;
-  if (used > 8ll * (long long)payload_len) return kDecRetryExact;
+  if (pos - pos0 > 8u * payload_len) return kDecRetryExact;
   return kDecOk;
 }
 

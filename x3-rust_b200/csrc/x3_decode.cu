@@ -273,32 +273,38 @@ __global__ void __launch_bounds__(256) crc_frames_kernel(const DecodeArgs a) {
 // ------------------------------------------------------------------------------------------------
 // 3. decode, one thread per frame
 // ------------------------------------------------------------------------------------------------
-constexpr int kRingWords = 36;  // 32 used (8 chunks of 16 B) + 4 pad: stride 144 B spreads lanes over banks
+constexpr int kRingWords = 36;  // 8 chunks of 16 B + a mirror of chunk slot 0 (so 12-byte reads never wrap): 144 B
 
-// Per-lane reader: the lane's payload streams through its own shared-memory ring, filled by cp.async
-// at least one block ahead of consumption (a block consumes at most 41 bytes).
+// Per-lane reader: the lane's payload streams through its own shared-memory ring, filled by cp.async at least
+// one block ahead of consumption (a block consumes at most 41 bytes).  There is no bit-buffer state: a 64-bit
+// window is read straight from the ring at any bit position (3 LDS + 3 PRMT + 2 SHF).
 struct RingReader {
   const unsigned char *g0;   // 16-byte aligned global address of chunk 0 (contains the payload's first byte)
   uint32_t *ring;
   const unsigned char *end;  // end of the stream buffer
   uint32_t issued;           // chunks issued so far
   uint32_t n_async;          // chunks [0, n_async) lie wholly inside the stream buffer
-  uint32_t k, carry, sh;
+  uint32_t pos0;             // bit position of the payload inside chunk 0
 
+  __device__ __forceinline__ void fill(uint32_t *slot, const unsigned char *src, bool async) {
+    if (async) {
+      cp_async16(slot, src);
+    } else {
+      for (int w = 0; w < 4; w++) {
+        uint32_t v = 0;
+        for (int b = 0; b < 4; b++)
+          if (src + 4 * w + b < end) v |= (uint32_t)src[4 * w + b] << (8 * b);
+        slot[w] = v;
+      }
+    }
+  }
   __device__ __forceinline__ void issue_to(uint32_t want) {
     while (issued < want) {
-      uint32_t *slot = ring + (issued & 7u) * 4u;
+      const uint32_t sl = issued & 7u;
       const unsigned char *src = g0 + 16ull * issued;
-      if (issued < n_async) {
-        cp_async16(slot, src);
-      } else {
-        for (int w = 0; w < 4; w++) {
-          uint32_t v = 0;
-          for (int b = 0; b < 4; b++)
-            if (src + 4 * w + b < end) v |= (uint32_t)src[4 * w + b] << (8 * b);
-          slot[w] = v;
-        }
-      }
+      const bool async = issued < n_async;
+      fill(ring + sl * 4u, src, async);
+      if (sl == 0u) fill(ring + 32, src, async);  // mirror
       issued++;
     }
     cp_async_commit();
@@ -310,23 +316,21 @@ struct RingReader {
     const uintptr_t span = (uintptr_t)stream_end - (uintptr_t)g0;
     n_async = (uint32_t)(span >> 4 > 0xffffffffull ? 0xffffffffull : span >> 4);
     issued = 0;
-    const uint32_t off0 = (uint32_t)((uintptr_t)payload & 15u);
-    k = off0 >> 2;
-    issue_to((4u * k + 112u + 15u) >> 4);
+    pos0 = 8u * (uint32_t)((uintptr_t)payload & 15u);
+    issue_to(((pos0 >> 3) + 112u + 15u) >> 4);
     cp_async_wait_all();
-    if (off0 & 2u) { sh = 16; carry = bswap32(ring[k & 31u]); k++; }
-    else { sh = 32; carry = 0; }
   }
-  __device__ __forceinline__ void block_begin() {
-    issue_to((4u * k + 112u + 15u) >> 4);
+  __device__ __forceinline__ uint32_t start_pos() const { return pos0; }
+  __device__ __forceinline__ void block_begin(uint32_t pos) {
+    issue_to(((pos >> 3) + 112u + 15u) >> 4);
     cp_async_wait_1();
   }
-  __device__ __forceinline__ uint32_t next() {
-    const uint32_t w = bswap32(ring[k & 31u]);
-    k++;
-    const uint32_t v = funnel_l(w, carry, sh);
-    carry = w;
-    return v;
+  __device__ __forceinline__ void fetch(uint32_t pos, uint32_t &hi, uint32_t &lo) const {
+    const uint32_t *q = ring + ((pos >> 5) & 31u);
+    const uint32_t a = bswap32(q[0]), b = bswap32(q[1]), c = bswap32(q[2]);
+    const uint32_t s = pos & 31u;
+    hi = funnel_l(b, a, s);
+    lo = funnel_l(c, b, s);
   }
 };
 

@@ -334,7 +334,7 @@ struct RingReader {
   }
 };
 
-__global__ void __launch_bounds__(kDecThreads) decode_frames_kernel(const DecodeArgs a) {
+__global__ void __launch_bounds__(kDecThreads, 5) decode_frames_kernel(const DecodeArgs a) {
   __shared__ __align__(16) uint32_t s_ring[kDecThreads * kRingWords];
   __shared__ __align__(16) uint32_t s_stage[kDecThreads * kStageWords];
   const int tid = threadIdx.x;

@@ -23,6 +23,9 @@ import sys
 import threading
 import time
 
+# stdout carries exactly one JSON line: keep NCCL's own banner / debug output on stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))

@@ -176,21 +176,24 @@ X3_HD uint32_t crc16_bytes(const uint16_t *T, const uint8_t *d, uint32_t n) {
 // Fast path
 // ------------------------------------------------------------------------------------------------
 
-// Reader concept (fast path): the payload is addressed by BIT POSITION, there is no bit-buffer state:
-//   uint32_t start_pos()                 bit position of the payload's first bit
-//   void block_begin(uint32_t pos)       called once per block (the device reader tops up its ring here)
-//   void fetch(pos, hi, lo)              the 64 bits that start at bit `pos` (big-endian numeric)
-// fetch may return bytes that lie after the payload; decode_frame_fast checks at the end that it never consumed
+// Reader concept (fast path).  The decoder only ever moves forward, at most 32 bits at a time:
+//   void block_begin()                   called once per block (the device reader tops up its ring here)
+//   void window(hi, lo)                  the 64 bits that start at the current bit position (big-endian numeric)
+//   void advance(n)                      consume n <= 32 bits
+//   uint32_t bits_used()                 bits consumed since the start of the payload
+// window() may show bytes that lie after the payload; decode_frame_fast checks at the end that it never consumed
 // a bit past the payload (the reference zero-fills there) and retries exactly if so.
 
 // Plain reader over memory (host simulation): assembles the window bytewise, zero past the buffer end.
 struct PlainBitReader {
   const uint8_t *payload;
   const uint8_t *end;
-  X3_HD void init(const uint8_t *p, const uint8_t *stream_end) { payload = p; end = stream_end; }
-  X3_HD uint32_t start_pos() const { return 0u; }
-  X3_HD void block_begin(uint32_t) {}
-  X3_HD void fetch(uint32_t pos, uint32_t &hi, uint32_t &lo) const {
+  uint32_t pos;
+  X3_HD void init(const uint8_t *p, const uint8_t *stream_end) { payload = p; end = stream_end; pos = 0; }
+  X3_HD void block_begin() {}
+  X3_HD void advance(uint32_t n) { pos += n; }
+  X3_HD uint32_t bits_used() const { return pos; }
+  X3_HD void window(uint32_t &hi, uint32_t &lo) const {
     const uint8_t *p = payload + (pos >> 3);
     uint32_t w[3];
     for (int k = 0; k < 3; k++) {
@@ -234,13 +237,11 @@ X3_HD bool frame_fast_eligible(uint32_t samples, uint32_t payload_len, uintptr_t
 // Returns kDecOk or kDecRetryExact.
 template <class Reader>
 X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint32_t samples, uint32_t *stage) {
-  const uint32_t pos0 = rd.start_pos();
-  uint32_t pos = pos0;
   uint32_t hi, lo;
-  rd.block_begin(pos);
-  rd.fetch(pos, hi, lo);
+  rd.block_begin();
+  rd.window(hi, lo);
   int32_t lw = (int32_t)(hi >> 16);        // first sample, decoder.rs:42 (only the low 16 bits of lw matter)
-  pos += 16;
+  rd.advance(16);
   uint32_t prev = (uint32_t)lw;            // last sample not yet written (low half of the next output word)
   bool bad = false;
 
@@ -248,15 +249,15 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
   uint4 *out4 = reinterpret_cast<uint4 *>(out);
 
   for (uint32_t b = 0; b < nblk; b++) {
-    rd.block_begin(pos);
+    rd.block_begin();
     const bool tail = (b == nblk - 1u);
     uint32_t *st = stage + (b & 3u) * 10u;
 
-    rd.fetch(pos, hi, lo);
+    rd.window(hi, lo);
     const uint32_t ftype = hi >> 30;
     if (ftype != 0u) {
       // ---- Rice block: z zeros, then nbk bits of which the first is the terminator ----
-      pos += 2;
+      rd.advance(2);
       const uint32_t nbk = ftype == 1u ? 1u : (ftype == 2u ? 2u : 4u);          // decoder.rs:158,180
       const int32_t level = ftype == 1u ? 1 : (ftype == 2u ? 2 : 8);            // 1<<nsubs of RICE1 / RICE3
       const uint32_t inv_len = ftype == 1u ? 16u : (ftype == 2u ? 26u : 60u);   // x3.rs:214,222,250
@@ -265,7 +266,7 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
       // A valid code is at most 10 bits, so three codes are parsed per 64-bit window.
 #pragma unroll
       for (int i = 0; i < 20; i++) {
-        if (i % 3 == 0) { rd.fetch(pos, hi, lo); cum = 0; }
+        if (i % 3 == 0) { rd.window(hi, lo); cum = 0; }
         if (i < 19 || !tail) {
           X3_RICE_SAMPLE();
           if ((i & 1) == 0) st[i >> 1] = (prev & 0xffffu) | ((uint32_t)lw << 16);
@@ -273,7 +274,7 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
         }
         if (i % 3 == 2 || i == 19) {
           cmax = cum > cmax ? cum : cmax;
-          pos += cum;
+          rd.advance(cum > 32u ? 32u : cum);  // a longer group is malformed for this path; `bad` is set below
         }
       }
       // out-of-range index (decoder.rs:161,187; includes every zero run the 32-bit peek cannot see the end of)
@@ -282,27 +283,27 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
       if (max_ip >= inv_len + (uint32_t)level || cmax > 32u) bad = true;
     } else {
       const uint32_t nb = ((hi >> 26) & 15u) + 1u;  // decoder.rs:211
-      pos += 6;
+      rd.advance(6);
       if (nb <= 5u) { bad = true; break; }           // FrameDecodeInvalidBPF, decoder.rs:213-216
       if (nb == 16u) {
         // ---- literal block: raw 16-bit samples ----
         for (int j = 0; j < 10; j++) {
-          rd.fetch(pos, hi, lo);
+          rd.window(hi, lo);
           lw = (int32_t)(hi >> 16);
           st[j] = (prev & 0xffffu) | ((uint32_t)lw << 16);
           if (j < 9 || !tail) {
             lw = (int32_t)(hi & 0xffffu);
             prev = (uint32_t)lw;
-            pos += 32;
+            rd.advance(32);
           } else {
-            pos += 16;
+            rd.advance(16);
           }
         }
       } else {
         // ---- BFP block: nb-bit two's complement differences (decoder.rs:224-231) ----
         const int32_t half = 1 << (nb - 1u), full = 1 << nb;
         for (int j = 0; j < 10; j++) {
-          rd.fetch(pos, hi, lo);
+          rd.window(hi, lo);
           int32_t v = (int32_t)(hi >> (32u - nb));
           if (v > half) v -= full;                    // unsigned_to_i16: strictly greater, decoder.rs:203
           lw += v;
@@ -312,9 +313,9 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
             if (v > half) v -= full;
             lw += v;
             prev = (uint32_t)lw;
-            pos += 2u * nb;
+            rd.advance(2u * nb);
           } else {
-            pos += nb;
+            rd.advance(nb);
           }
         }
       }
@@ -332,7 +333,7 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
   if (bad) return kDecRetryExact;
   // bits consumed must lie inside the payload (the reference zero-fills past the end; we may have read
   // the next frame's bytes there instead)
-  if (pos - pos0 > 8u * payload_len) return kDecRetryExact;
+  if (rd.bits_used() > 8u * payload_len) return kDecRetryExact;
   return kDecOk;
 }
 

@@ -273,42 +273,41 @@ __global__ void __launch_bounds__(256) crc_frames_kernel(const DecodeArgs a) {
 // ------------------------------------------------------------------------------------------------
 // 3. decode, one thread per frame
 // ------------------------------------------------------------------------------------------------
-constexpr int kRingWords = 36;  // 8 chunks of 16 B + a mirror of chunk slot 0 (so 12-byte reads never wrap): 144 B
+constexpr int kRingWords = 36;  // 8 chunks of 16 B (32 words) + 4 words of padding so lanes spread over banks: 144 B
 
 // Per-lane reader: the lane's payload streams through its own shared-memory ring, filled by cp.async at least
-// one block ahead of consumption (a block consumes at most 41 bytes).  There is no bit-buffer state: a 64-bit
-// window is read straight from the ring at any bit position (3 LDS + 3 PRMT + 2 SHF).
+// one block ahead of consumption (a block consumes at most 41 bytes).  Four consecutive big-endian words
+// A,B,C,D are kept in registers; the 64-bit window at the current bit position is two funnel shifts of them, and
+// when the position crosses a word boundary they shift by one and the next D is loaded -- one full step before it
+// can be needed, so the shared-memory latency is off the decoder's dependency chain.
 struct RingReader {
   const unsigned char *g0;   // 16-byte aligned global address of chunk 0 (contains the payload's first byte)
   uint32_t *ring;
   const unsigned char *end;  // end of the stream buffer
   uint32_t issued;           // chunks issued so far
   uint32_t n_async;          // chunks [0, n_async) lie wholly inside the stream buffer
-  uint32_t pos0;             // bit position of the payload inside chunk 0
+  uint32_t pos0, pos;        // bit positions relative to chunk 0: payload start, current
+  uint32_t A, B, C, D;       // big-endian words w, w+1, w+2, w+3 with w = pos >> 5
 
-  __device__ __forceinline__ void fill(uint32_t *slot, const unsigned char *src, bool async) {
-    if (async) {
-      cp_async16(slot, src);
-    } else {
-      for (int w = 0; w < 4; w++) {
-        uint32_t v = 0;
-        for (int b = 0; b < 4; b++)
-          if (src + 4 * w + b < end) v |= (uint32_t)src[4 * w + b] << (8 * b);
-        slot[w] = v;
-      }
-    }
-  }
   __device__ __forceinline__ void issue_to(uint32_t want) {
     while (issued < want) {
-      const uint32_t sl = issued & 7u;
+      uint32_t *slot = ring + (issued & 7u) * 4u;
       const unsigned char *src = g0 + 16ull * issued;
-      const bool async = issued < n_async;
-      fill(ring + sl * 4u, src, async);
-      if (sl == 0u) fill(ring + 32, src, async);  // mirror
+      if (issued < n_async) {
+        cp_async16(slot, src);
+      } else {
+        for (int w = 0; w < 4; w++) {
+          uint32_t v = 0;
+          for (int b = 0; b < 4; b++)
+            if (src + 4 * w + b < end) v |= (uint32_t)src[4 * w + b] << (8 * b);
+          slot[w] = v;
+        }
+      }
       issued++;
     }
     cp_async_commit();
   }
+  __device__ __forceinline__ uint32_t word(uint32_t w) const { return bswap32(ring[w & 31u]); }
   __device__ __forceinline__ void start(const uint8_t *payload, const uint8_t *stream_end, uint32_t *ring_) {
     ring = ring_;
     end = stream_end;
@@ -316,22 +315,32 @@ struct RingReader {
     const uintptr_t span = (uintptr_t)stream_end - (uintptr_t)g0;
     n_async = (uint32_t)(span >> 4 > 0xffffffffull ? 0xffffffffull : span >> 4);
     issued = 0;
-    pos0 = 8u * (uint32_t)((uintptr_t)payload & 15u);
-    issue_to(((pos0 >> 3) + 112u + 15u) >> 4);
+    pos0 = pos = 8u * (uint32_t)((uintptr_t)payload & 15u);
+    issue_to(((pos >> 3) + 112u + 15u) >> 4);
     cp_async_wait_all();
+    const uint32_t w = pos >> 5;
+    A = word(w); B = word(w + 1); C = word(w + 2); D = word(w + 3);
   }
-  __device__ __forceinline__ uint32_t start_pos() const { return pos0; }
-  __device__ __forceinline__ void block_begin(uint32_t pos) {
+  __device__ __forceinline__ void block_begin() {
     issue_to(((pos >> 3) + 112u + 15u) >> 4);
     cp_async_wait_1();
   }
-  __device__ __forceinline__ void fetch(uint32_t pos, uint32_t &hi, uint32_t &lo) const {
-    const uint32_t *q = ring + ((pos >> 5) & 31u);
-    const uint32_t a = bswap32(q[0]), b = bswap32(q[1]), c = bswap32(q[2]);
+  __device__ __forceinline__ void window(uint32_t &hi, uint32_t &lo) const {
     const uint32_t s = pos & 31u;
-    hi = funnel_l(b, a, s);
-    lo = funnel_l(c, b, s);
+    hi = funnel_l(B, A, s);
+    lo = funnel_l(C, B, s);
   }
+  __device__ __forceinline__ void advance(uint32_t n) {  // n <= 32: crosses at most one word boundary
+    const uint32_t np = pos + n;
+    const bool cross = (np >> 5) != (pos >> 5);
+    const uint32_t nd = word((np >> 5) + 3u);   // only used when crossing; the ring slot is valid either way
+    A = cross ? B : A;
+    B = cross ? C : B;
+    C = cross ? D : C;
+    D = cross ? nd : D;
+    pos = np;
+  }
+  __device__ __forceinline__ uint32_t bits_used() const { return pos - pos0; }
 };
 
 __global__ void __launch_bounds__(kDecThreads, 5) decode_frames_kernel(const DecodeArgs a) {

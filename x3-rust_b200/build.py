@@ -26,6 +26,7 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "-Xcompiler", "-fPIC", "-shared", "-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd += os.environ.get("X3_NVCC_FLAGS", "").split()
     if verbose:
         cmd += ["-Xptxas", "-v"]
     subprocess.check_call(cmd)

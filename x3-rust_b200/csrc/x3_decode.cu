@@ -343,7 +343,7 @@ struct RingReader {
   __device__ __forceinline__ uint32_t bits_used() const { return pos - pos0; }
 };
 
-__global__ void __launch_bounds__(kDecThreads, 5) decode_frames_kernel(const DecodeArgs a) {
+__global__ void __launch_bounds__(kDecThreads, X3_DEC_MINBLOCKS) decode_frames_kernel(const DecodeArgs a) {
   __shared__ __align__(16) uint32_t s_ring[kDecThreads * kRingWords];
   __shared__ __align__(16) uint32_t s_stage[kDecThreads * kStageWords];
   const int tid = threadIdx.x;

@@ -11,7 +11,13 @@ namespace x3 {
 
 constexpr int kEncThreads = 512;       // generic kernel
 constexpr int kEncFastThreads = 544;   // fast kernel: 16 worker warps + 1 control warp
-constexpr int kDecThreads = 128;
+#ifndef X3_DEC_THREADS
+#define X3_DEC_THREADS 128
+#endif
+#ifndef X3_DEC_MINBLOCKS
+#define X3_DEC_MINBLOCKS 5
+#endif
+constexpr int kDecThreads = X3_DEC_THREADS;
 constexpr int kScanThreads = 256;
 
 struct EncodeArgs {

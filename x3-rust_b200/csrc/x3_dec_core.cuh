@@ -208,7 +208,8 @@ struct PlainBitReader {
 };
 
 constexpr uint32_t kFastGroup = 80;        // samples per staged flush (4 blocks of 20 = 160 B = 5 whole sectors)
-constexpr uint32_t kStageWords = 44;       // per-thread staging stride in words (176 B: conflict-free LDS.128)
+constexpr uint32_t kStageWords = 40;       // staged words per thread; word j of thread t lives at stage[j*stride] with
+                                           // stride = threads per CTA on the device (conflict-free 32-bit accesses), 1 on the host
 
 // Fast-path eligibility of a frame (Parameters::default() is checked by the caller).
 X3_HD bool frame_fast_eligible(uint32_t samples, uint32_t payload_len, uintptr_t payload_addr, uintptr_t out_addr) {
@@ -233,10 +234,11 @@ X3_HD bool frame_fast_eligible(uint32_t samples, uint32_t payload_len, uintptr_t
     if (i & 1u) lw -= (int32_t)i;                                                     \
   }
 
-// Decode one frame.  `stage` = this thread's 44-word staging area (16-byte aligned).
+// Decode one frame.  `stage` = this thread's staging area: 40 words, `ss` words apart.
 // Returns kDecOk or kDecRetryExact.
 template <class Reader>
-X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint32_t samples, uint32_t *stage) {
+X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint32_t samples, uint32_t *stage,
+                            const uint32_t ss) {
   uint32_t hi, lo;
   rd.block_begin();
   rd.window(hi, lo);
@@ -251,7 +253,7 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
   for (uint32_t b = 0; b < nblk; b++) {
     rd.block_begin();
     const bool tail = (b == nblk - 1u);
-    uint32_t *st = stage + (b & 3u) * 10u;
+    uint32_t *st = stage + (b & 3u) * 10u * ss;
 
     rd.window(hi, lo);
     const uint32_t ftype = hi >> 30;
@@ -269,7 +271,7 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
         if (i % 3 == 0) { rd.window(hi, lo); cum = 0; }
         if (i < 19 || !tail) {
           X3_RICE_SAMPLE();
-          if ((i & 1) == 0) st[i >> 1] = (prev & 0xffffu) | ((uint32_t)lw << 16);
+          if ((i & 1) == 0) st[(i >> 1) * ss] = (prev & 0xffffu) | ((uint32_t)lw << 16);
           else prev = (uint32_t)lw;
         }
         if (i % 3 == 2 || i == 19) {
@@ -290,7 +292,7 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
         for (int j = 0; j < 10; j++) {
           rd.window(hi, lo);
           lw = (int32_t)(hi >> 16);
-          st[j] = (prev & 0xffffu) | ((uint32_t)lw << 16);
+          st[j * ss] = (prev & 0xffffu) | ((uint32_t)lw << 16);
           if (j < 9 || !tail) {
             lw = (int32_t)(hi & 0xffffu);
             prev = (uint32_t)lw;
@@ -307,7 +309,7 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
           int32_t v = (int32_t)(hi >> (32u - nb));
           if (v > half) v -= full;                    // unsigned_to_i16: strictly greater, decoder.rs:203
           lw += v;
-          st[j] = (prev & 0xffffu) | ((uint32_t)lw << 16);
+          st[j * ss] = (prev & 0xffffu) | ((uint32_t)lw << 16);
           if (j < 9 || !tail) {
             v = (int32_t)(funnel_l(lo, hi, nb) >> (32u - nb));
             if (v > half) v -= full;
@@ -324,10 +326,13 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
     // ---- every fourth block: 160 staged bytes -> five whole 32-byte sectors of the output.  (Flushing 80 bytes
     // every second block was measured: the half-written sectors cost ~10 % extra DRAM traffic and it was slower.)
     if ((b & 3u) == 3u) {
-      const uint4 *s4 = reinterpret_cast<const uint4 *>(stage);
       uint4 *o = out4 + (size_t)(b >> 2) * 10u;
 #pragma unroll
-      for (int q = 0; q < 10; q++) o[q] = s4[q];
+      for (int q = 0; q < 10; q++) {
+        uint4 v;
+        v.x = stage[(4 * q) * ss]; v.y = stage[(4 * q + 1) * ss]; v.z = stage[(4 * q + 2) * ss]; v.w = stage[(4 * q + 3) * ss];
+        o[q] = v;
+      }
     }
   }
   if (bad) return kDecRetryExact;

@@ -273,7 +273,8 @@ __global__ void __launch_bounds__(256) crc_frames_kernel(const DecodeArgs a) {
 // ------------------------------------------------------------------------------------------------
 // 3. decode, one thread per frame
 // ------------------------------------------------------------------------------------------------
-constexpr int kRingWords = 36;  // 8 chunks of 16 B (32 words) + 4 words of padding so lanes spread over banks: 144 B
+constexpr int kRingWords = 36;  // 8 chunks of 16 B (32 words) + 4 words of padding: 144 B.  (An odd stride of 33 words with
+                                // 4-byte cp.async removes the 4-way bank conflict of the ring reads but was measured slower.)
 
 // Per-lane reader: the lane's payload streams through its own shared-memory ring, filled by cp.async at least
 // one block ahead of consumption (a block consumes at most 41 bytes).  Four consecutive big-endian words
@@ -345,7 +346,7 @@ struct RingReader {
 
 __global__ void __launch_bounds__(kDecThreads, X3_DEC_MINBLOCKS) decode_frames_kernel(const DecodeArgs a) {
   __shared__ __align__(16) uint32_t s_ring[kDecThreads * kRingWords];
-  __shared__ __align__(16) uint32_t s_stage[kDecThreads * kStageWords];
+  __shared__ __align__(16) uint32_t s_stage[kDecThreads * kStageWords];  // [word][thread]
   const int tid = threadIdx.x;
   const unsigned long long n = *a.n_frames < a.max_frames ? *a.n_frames : a.max_frames;
   const bool dflt = a.P.block_len == 20 && a.P.codes[0] == 0 && a.P.codes[1] == 1 && a.P.codes[2] == 3;
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(kDecThreads, X3_DEC_MINBLOCKS) decode_frames_k
         if (dflt && frame_fast_eligible(fr.samples, fr.payload_len, (uintptr_t)pl, (uintptr_t)out)) {
           RingReader rd;
           rd.start(pl, stream_end, s_ring + tid * kRingWords);
-          r = decode_frame_fast(rd, fr.payload_len, out, fr.samples, s_stage + tid * kStageWords);
+          r = decode_frame_fast(rd, fr.payload_len, out, fr.samples, s_stage + tid, (uint32_t)kDecThreads);
           cp_async_wait_all();
         }
         if (r == kDecRetryExact) r = decode_frame_exact(pl, fr.payload_len, out, fr.samples, a.P);

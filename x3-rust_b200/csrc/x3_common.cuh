@@ -127,6 +127,18 @@ X3_HD uint32_t crc16_half(const uint16_t *T, uint32_t s, uint32_t h) {
 X3_HD uint32_t crc16_byte(const uint16_t *T, uint32_t s, uint32_t b) {
   return ((s << 8) & 0xffffu) ^ (uint32_t)T[((s >> 8) ^ b) & 0xff];
 }
+// Table-free variants for kernels that are bound by shared-memory lookups.  With P = x^16+x^12+x^5+1,
+// a*x^16 mod P for a 16-bit a is r = low16(q<<12 ^ q<<5 ^ q), where the quotient q solves q = a ^ q>>4 ^ q>>11,
+// i.e. q = a ^ a>>4 ^ a>>8 ^ a>>12 ^ a>>11 (the q>>15 terms cancel).  Ten ALU operations per 16 bits.
+X3_HD uint32_t crc16_mulx16(uint32_t a) {  // a < 2^16
+  const uint32_t q = a ^ (a >> 4) ^ (a >> 8) ^ (a >> 12) ^ (a >> 11);
+  return ((q << 12) ^ (q << 5) ^ q) & 0xffffu;
+}
+X3_HD uint32_t crc16_word_alu(uint32_t s, uint32_t w) {  // same result as crc16_word
+  const uint32_t s1 = crc16_mulx16((s ^ (w >> 16)) & 0xffffu) ^ (w & 0xffffu);
+  return crc16_mulx16(s1);
+}
+X3_HD uint32_t crc16_half_alu(uint32_t s, uint32_t h) { return crc16_mulx16((s ^ h) & 0xffffu); }
 // multiply a 16-bit state by the constant whose (lo,hi) table pair starts at table index t
 X3_HD uint32_t crc16_mulc(const uint16_t *T, int t, uint32_t s) {
   return (uint32_t)T[t * 256 + (s & 0xff)] ^ (uint32_t)T[(t + 1) * 256 + ((s >> 8) & 0xff)];

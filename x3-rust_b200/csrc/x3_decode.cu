@@ -57,6 +57,31 @@ __device__ bool header_valid(const uint8_t *p, const uint16_t *T, Cand &c) {
   return true;
 }
 
+// nonzero iff one of the two halfwords of w is the frame key (bytes 78 33 in memory order); may report a false
+// positive (borrow out of a zero low halfword), which examine_piece sorts out
+__device__ __forceinline__ uint32_t haskey(uint32_t w) {
+  const uint32_t x = w ^ 0x33783378u;
+  return (x - 0x00010001u) & ~x & 0x80008000u;
+}
+
+// rare path: a 16-byte piece that contains the key somewhere
+__device__ __noinline__ void examine_piece(const ScanArgs &a, const uint16_t *s_T, Cand *s_cand, unsigned int *s_count,
+                                           unsigned long long t0, unsigned long long o, uint4 v) {
+  const uint32_t xs[4] = {v.x ^ 0x33783378u, v.y ^ 0x33783378u, v.z ^ 0x33783378u, v.w ^ 0x33783378u};
+  for (int j = 0; j < 4; j++) {
+    for (int hsel = 0; hsel < 2; hsel++) {
+      if (((xs[j] >> (16 * hsel)) & 0xffffu) != 0u) continue;
+      const unsigned long long p = o + 4u * j + 2u * hsel;
+      if (p + kFrameHeaderLen > a.stream_len) continue;
+      Cand c;
+      if (!header_valid(a.stream + p, s_T, c)) continue;
+      c.off = (uint32_t)(p - t0);
+      const unsigned int idx = atomicAdd(s_count, 1u);
+      if (idx < kScanCap) s_cand[idx] = c;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kScanThreads) scan_headers_kernel(const ScanArgs a) {
   __shared__ uint16_t s_T[512];  // T_0, T_1 of the CRC bank are enough for halfword updates
   __shared__ Cand s_cand[kScanCap];
@@ -77,29 +102,28 @@ __global__ void __launch_bounds__(kScanThreads) scan_headers_kernel(const ScanAr
     const unsigned long long t1 = t0 + kScanTileBytes < a.stream_len ? t0 + kScanTileBytes : a.stream_len;
 
     // ---- candidates: halfword 'x','3' at an even offset with a valid header behind it ----
-    for (unsigned long long o = t0 + (unsigned long long)tid * 16u; o < t1; o += (unsigned long long)kScanThreads * 16u) {
-      uint32_t q[4] = {0u, 0u, 0u, 0u};
-      if (o + 16u <= a.stream_len) {
-        const uint4 v = *reinterpret_cast<const uint4 *>(a.stream + o);
-        q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w;
-      } else {
-        for (unsigned long long b = o; b < a.stream_len; b++) q[(b - o) >> 2] |= (uint32_t)a.stream[b] << (8u * ((b - o) & 3u));
+    // Whole 16-byte pieces, four independent loads in flight per thread; key hits are rare and handled out of line.
+    {
+      const unsigned long long t1v = t0 + ((t1 - t0) & ~15ull);  // end of the whole 16-byte pieces of this tile
+      const unsigned long long step = (unsigned long long)kScanThreads * 16u;
+      unsigned long long o = t0 + (unsigned long long)tid * 16u;
+#define X3_KEYTEST(v) (haskey((v).x) | haskey((v).y) | haskey((v).z) | haskey((v).w))
+      for (; o + 3u * step < t1v; o += 4u * step) {
+        const uint4 v0 = *reinterpret_cast<const uint4 *>(a.stream + o);
+        const uint4 v1 = *reinterpret_cast<const uint4 *>(a.stream + o + step);
+        const uint4 v2 = *reinterpret_cast<const uint4 *>(a.stream + o + 2u * step);
+        const uint4 v3 = *reinterpret_cast<const uint4 *>(a.stream + o + 3u * step);
+        if (X3_KEYTEST(v0)) examine_piece(a, s_T, s_cand, &s_count, t0, o, v0);
+        if (X3_KEYTEST(v1)) examine_piece(a, s_T, s_cand, &s_count, t0, o + step, v1);
+        if (X3_KEYTEST(v2)) examine_piece(a, s_T, s_cand, &s_count, t0, o + 2u * step, v2);
+        if (X3_KEYTEST(v3)) examine_piece(a, s_T, s_cand, &s_count, t0, o + 3u * step, v3);
       }
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const uint32_t x = q[j] ^ 0x33783378u;  // bytes 78 33 in memory order
-        if (((x - 0x00010001u) & ~x & 0x80008000u) == 0u) continue;  // no zero halfword
-#pragma unroll
-        for (int hsel = 0; hsel < 2; hsel++) {
-          if (((x >> (16 * hsel)) & 0xffffu) != 0u) continue;
-          const unsigned long long p = o + 4u * j + 2u * hsel;
-          if (p + kFrameHeaderLen > a.stream_len) continue;
-          Cand c;
-          if (!header_valid(a.stream + p, s_T, c)) continue;
-          c.off = (uint32_t)(p - t0);
-          const unsigned int idx = atomicAdd(&s_count, 1u);
-          if (idx < kScanCap) s_cand[idx] = c;
-        }
+      for (; o < t1v; o += step) {
+        const uint4 v0 = *reinterpret_cast<const uint4 *>(a.stream + o);
+        if (X3_KEYTEST(v0)) examine_piece(a, s_T, s_cand, &s_count, t0, o, v0);
+      }
+#undef X3_KEYTEST
+      if (tid == 0 && t1v < t1) {  // fewer than 16 bytes left: no header fits, nothing to find
       }
     }
     __syncthreads();
@@ -238,10 +262,10 @@ __global__ void __launch_bounds__(256) crc_frames_kernel(const DecodeArgs a) {
             if (((uintptr_t)q & 3u) == 0) {
               const uint32_t *q4 = reinterpret_cast<const uint32_t *>(q);
 #pragma unroll
-              for (int w = 0; w < 4; w++) cs = crc16_word(s_T, cs, bswap32(q4[w]));
+              for (int w = 0; w < 4; w++) cs = crc16_word_alu(cs, bswap32(q4[w]));
             } else {
 #pragma unroll
-              for (int w = 0; w < 4; w++) cs = crc16_word(s_T, cs, load_be32_2aligned(q + 4 * w));
+              for (int w = 0; w < 4; w++) cs = crc16_word_alu(cs, load_be32_2aligned(q + 4 * w));
             }
             h = crc16_mulc(s_T, 4, h) ^ cs;
           }

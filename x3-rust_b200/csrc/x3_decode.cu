@@ -25,7 +25,7 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // 1. frame index
 // ------------------------------------------------------------------------------------------------
-constexpr int kScanCap = 512;                 // candidates per 64 KiB tile before falling back
+constexpr int kScanCap = 1024;                // candidates per 128 KiB tile before falling back
 constexpr int kCountShift = 38;               // look-back value = (frames << 38) | samples
 
 struct Cand {

@@ -78,7 +78,7 @@ struct ScanArgs {
   const uint16_t *crc_tables;
   uint32_t n_tiles;
 };
-constexpr uint32_t kScanTileBytes = 64 * 1024;
+constexpr uint32_t kScanTileBytes = 128 * 1024;
 cudaError_t launch_scan(const ScanArgs &a, cudaStream_t stream);
 cudaError_t launch_chain_check(const ScanArgs &a, cudaStream_t stream);
 

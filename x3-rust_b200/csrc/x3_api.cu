@@ -287,7 +287,7 @@ int x3_encode_device(const int16_t *d_pcm, size_t n_samples, const x3_params *p,
 
   const unsigned long long nf = (n_samples + d.P.spf - 1) / d.P.spf;
   if (nf > 0xfffffff0ull) return X3_ERR_UNSUPPORTED_PARAMS;
-  const size_t ws_bytes = 128 + 8 * (size_t)nf;
+  const size_t ws_bytes = 128 + 8 * (size_t)nf + 256;  // + 32 words of optional phase timing (X3_ENC_TIMING)
   unsigned char *ws = nullptr;
   CU(cudaMallocAsync(&ws, ws_bytes, st));
   cudaError_t e = cudaMemsetAsync(ws, 0, ws_bytes, st);
@@ -305,6 +305,7 @@ int x3_encode_device(const int16_t *d_pcm, size_t n_samples, const x3_params *p,
   a.result = reinterpret_cast<unsigned long long *>(ws);        // 8 words
   a.ticket = reinterpret_cast<unsigned int *>(ws + 64);
   a.status = reinterpret_cast<unsigned long long *>(ws + 128);
+  a.timing = reinterpret_cast<unsigned long long *>(ws + 128 + 8 * (size_t)nf);
   a.crc_tables = ds->crc_dev;
 
   // the fast kernel stages frames with 16-byte cp.async: it needs a 16-byte aligned base and frame size
@@ -327,10 +328,24 @@ int x3_encode_device(const int16_t *d_pcm, size_t n_samples, const x3_params *p,
   tm.stop();
   g_launches++;
   if (e == cudaSuccess) e = cudaMemcpyAsync(host_res, ws, 64, cudaMemcpyDeviceToHost, st);
+#ifdef X3_ENC_TIMING
+  if (e == cudaSuccess) e = cudaMemcpyAsync(host_res + 16, ws + 128 + 8 * (size_t)nf, 256, cudaMemcpyDeviceToHost, st);
+#endif
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   cudaFreeAsync(ws, st);
   if (e != cudaSuccess) return cuda_fail(e, "encode_frames_kernel");
   tl_ms[0] = tl_ms[2] = tm.ms();
+#ifdef X3_ENC_TIMING
+  {
+    const char *names[] = {"waitA", "measure", "waitB", "scan2", "pack", "waitD", "or", "waitE", "crc", "waitOff", "copy", "frames",
+                           "c_waitSize", "c_hist", "c_poll", "c_waitCrc", "c_final", "c_frames"};
+    fprintf(stderr, "[x3 timing] cycles per frame:");
+    for (int k = 0; k < 11; k++) fprintf(stderr, " %s=%.0f", names[k], (double)host_res[16 + k] / (double)(host_res[16 + 11] ? host_res[16 + 11] : 1));
+    fprintf(stderr, " |");
+    for (int k = 12; k < 17; k++) fprintf(stderr, " %s=%.0f", names[k], (double)host_res[16 + k] / (double)(host_res[16 + 17] ? host_res[16 + 17] : 1));
+    fprintf(stderr, "\n");
+  }
+#endif
   *out_len = (size_t)host_res[0];
   if (stats)
     for (int k = 0; k < 6; k++) stats->samples_by_mode[k] = host_res[2 + k];

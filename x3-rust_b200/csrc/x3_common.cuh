@@ -101,6 +101,7 @@ X3_HD uint32_t clz_shift(uint32_t x) {
 
 // zig-zag fold of the first difference: u = d<0 ? -2d-1 : 2d  (closed form of the `offset` indexing of
 // x3.rs:207-252, verified against the four tables by tests/test_oracle_golden.py)
+// (a widening multiply -- mul.wide.s32 d,2 -> 2d and the sign mask in one IMAD.WIDE -- was measured: much slower)
 X3_HD uint32_t fold(int32_t d) { return ((uint32_t)d << 1) ^ (uint32_t)(d >> 31); }
 // INV_RICE_CODE[i], x3.rs:200-204
 X3_HD int32_t unfold(uint32_t i) { return (int32_t)(i >> 1) ^ -(int32_t)(i & 1u); }

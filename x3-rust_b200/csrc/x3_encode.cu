@@ -330,6 +330,12 @@ __device__ __forceinline__ void stage_frame_fast(const int16_t *pcm, unsigned lo
   cp_async_commit();
 }
 
+#ifdef X3_ENC_TIMING
+#define X3_T(k) { const long long now__ = clock64(); tacc[k] += now__ - tlast; tlast = now__; }
+#else
+#define X3_T(k)
+#endif
+
 __device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 1, 512;\n" ::: "memory"); }
 // barrier ids are immediates so that ptxas reserves exactly the eight barriers used (not all sixteen)
 __device__ __forceinline__ void bar_sync_all(int id) {
@@ -346,7 +352,8 @@ __device__ __forceinline__ void bar_sync_all(int id) {
   }
 }
 __device__ __forceinline__ void bar_arrive_all(int id) {
-  __threadfence_block();
+  // bar.arrive orders this thread's prior shared-memory writes for the threads that bar.sync on the same barrier
+  // (the PTX producer/consumer idiom); an explicit MEMBAR here cost ~600 cycles per frame
   switch (id) {
     case 2: asm volatile("bar.arrive 2, 544;\n" ::: "memory"); break;
     case 3: asm volatile("bar.arrive 3, 544;\n" ::: "memory"); break;
@@ -485,30 +492,19 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
 
   if (!worker) {
     // ================================ control warp ================================
-    uint32_t mode_blocks[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+#ifdef X3_ENC_TIMING
+    long long tacc[12] = {0}, tlast = clock64();
+    unsigned long long cframes = 0;
+#endif
     for (uint32_t par = 0;; par = (par + 1u == NB ? 0u : par + 1u)) {
       uint32_t *info = s_misc + 48 + 8 * par;
       bar_sync_all(kBarSize + par);
+      X3_T(0)
       const uint32_t f = info[0];
       if (f == kNoFrame) break;
       const uint32_t n = info[1], payload_len = info[2];
       const uint32_t frame_bytes = (uint32_t)kFrameHeaderLen + payload_len;
-      {
-        // histogram of the 512 per-block stats bytes: each lane counts its 16 bytes per mode (exact zero-byte test)
-        const uint4 sq = reinterpret_cast<const uint4 *>(s_stat + par * 512)[lane];
-        const uint32_t w4[4] = {sq.x, sq.y, sq.z, sq.w};
-#pragma unroll
-        for (int m = 0; m < 6; m++) {
-          uint32_t c = 0;
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const uint32_t x = w4[k] ^ (0x01010101u * (uint32_t)m);
-            const uint32_t t = ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu);  // 0x80 in every zero byte
-            c += __popc(t);
-          }
-          mode_blocks[m] += c;
-        }
-      }
+      X3_T(1)
       // this frame's byte offset: wait for the scanner to turn the published size into a prefix
       unsigned long long pv = 0;
       if (lane == 0) {
@@ -518,7 +514,9 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
       const unsigned long long excl = (pv & kValueMask) - frame_bytes;
       const bool fits = excl + frame_bytes <= a.out_cap;
       if (lane == 0 && !fits) atomicMax(a.result + 1, 1ull);         // ByteWriterInsufficientMemory, bytewriter.rs:88
+      X3_T(2)
       bar_sync_all(kBarCrc + par);
+      X3_T(3)
       // payload CRC = sum_j V_j * x^(4096 j), then the tail bytes, then the header
       const uint32_t *s_words = s_img + par * img_words;
       const uint32_t *V = s_V + par * kMaxSlices;
@@ -552,14 +550,17 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
       }
       __syncwarp();
       bar_arrive_all(kBarOff + par);
+      X3_T(4)
+#ifdef X3_ENC_TIMING
+      cframes++;
+#endif
     }
-#pragma unroll
-    for (int m = 0; m < 6; m++) {
-      uint32_t c = mode_blocks[m];
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-      if (lane == 0 && c) atomicAdd(a.result + 2 + m, (unsigned long long)c * BL);
+#ifdef X3_ENC_TIMING
+    if (lane == 0) {
+      for (int k = 0; k < 5; k++) atomicAdd(a.timing + 12 + k, (unsigned long long)tacc[k]);
+      atomicAdd(a.timing + 17, cframes);
     }
+#endif
     return;
   }
 
@@ -573,6 +574,10 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
     stage_frame_fast(a.pcm, s00, r0 < a.P.spf ? (uint32_t)r0 : a.P.spf, s_in, tid);
   }
   uint32_t it = 0, par = 0;
+  unsigned long long stat_acc = 0;
+#ifdef X3_ENC_TIMING
+  long long tacc[12] = {0}, tlast = clock64();
+#endif
   uint32_t hist_len[NB];  // payload lengths of the frames still held in the image ring
 #pragma unroll
   for (uint32_t q = 0; q < NB; q++) hist_len[q] = 0;
@@ -586,6 +591,7 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
 
     cp_async_wait_all();
     bar_workers();  // (A) samples staged
+    X3_T(0)
 
     // ---- measure ----
     const uint32_t b = tid;
@@ -607,9 +613,9 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
       }
       if (b == 0) nbits += 16;  // <Audio State>, encoder.rs:189
     }
-    // statistics (stats[ftype] += block.len(), encoder.rs:199): full blocks leave one byte for the control
-    // warp to histogram; the rare short block adds its length directly
-    s_stat[par * 512 + tid] = (unsigned char)((active && len == BL) ? mode.stat : 7u);
+    // statistics (stats[ftype] += block.len(), encoder.rs:199): every thread counts its own full blocks per mode;
+    // the rare short block adds its length directly
+    if (active && len == BL) stat_acc += 1ull << (10u * mode.stat);   // six 10-bit block counters per thread
     if (active && len != BL && len > 0) atomicAdd(&s_misc[40 + mode.stat], len);
     uint32_t incl = nbits;
 #pragma unroll
@@ -618,8 +624,10 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
       if (lane >= d) incl += t;
     }
     if (lane == 31) s_misc[wid] = incl;
+    X3_T(1)
     bar_workers();  // (B) warp totals visible; all reads of s_in by the fast path are done
 
+    X3_T(2)
     const uint32_t wt = lane < NWW ? s_misc[lane] : 0u;
     uint32_t wincl = wt;
 #pragma unroll
@@ -636,6 +644,7 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
       st_status(a.status + f, kFlagAgg | (unsigned long long)(kFrameHeaderLen + payload_len));
     }
     bar_arrive_all(kBarSize + par);  // -> control: frame size known
+    X3_T(3)
 
     // ---- prefetch the next frame, pack this one ----
     const uint32_t warp_base = __shfl_sync(0xffffffffu, wincl - wt, wid);
@@ -655,11 +664,15 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
       }
     }
     if (tid == 0) s_misc[32] = atomicAdd(a.ticket, 1u);  // this CTA's next frame
+    X3_T(4)
     bar_workers();  // (D) every plain store done
+    X3_T(5)
     uint32_t f_next = s_misc[32];
     if (f_next >= a.n_frames) f_next = kNoFrame;
     if (active && (bit_off & 31u)) atomicOr(&s_words[bit_off >> 5], s_first[tid]);
+    X3_T(6)
     bar_workers();  // (E) payload image complete
+    X3_T(7)
     // stage the next frame now: s_in has been free since barrier (B), and the copy lands while the CRC and
     // the copy-out run
     if (f_next != kNoFrame) {
@@ -695,6 +708,7 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
       }
     }
     bar_arrive_all(kBarCrc + par);  // -> control: slice CRCs and image complete
+    X3_T(8)
 
     // ---- the oldest frame in the ring goes out now: its offset has had NB-1 frame times to arrive ----
 #pragma unroll
@@ -703,6 +717,7 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
     if (it >= NB - 1) {
       const uint32_t q = par + 1u == NB ? 0u : par + 1u;  // the buffer the next frame will reuse
       bar_sync_all(kBarOff + q);
+      X3_T(9)
       const uint32_t *info = s_misc + 48 + 8 * q;
       uint32_t L = 0;
 #pragma unroll
@@ -712,10 +727,19 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
         const unsigned long long off = (unsigned long long)info[4] | ((unsigned long long)info[5] << 32);
         copy_payload_out(a.out + off + kFrameHeaderLen, s_img + q * img_words, L, tid);
       }
+      X3_T(10)
     }
     f = f_next;
     it++;
     par = par + 1u == NB ? 0u : par + 1u;
+    if ((it & 1023u) == 1023u) {  // the 10-bit fields are about to fill up
+#pragma unroll
+      for (int m = 0; m < 6; m++) {
+        const uint32_t c = (uint32_t)(stat_acc >> (10 * m)) & 1023u;
+        if (c) atomicAdd(&s_misc[40 + m], c * BL);
+      }
+      stat_acc = 0;
+    }
   }
   // ---- drain: the frames still in the ring, oldest first, then tell the control warp to stop ----
   {
@@ -736,6 +760,17 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
     }
     if (tid == 0) s_misc[48 + 8 * par] = kNoFrame;
     bar_arrive_all(kBarSize + par);
+  }
+#ifdef X3_ENC_TIMING
+  if (tid == 0) {
+    for (int k = 0; k < 11; k++) atomicAdd(a.timing + k, (unsigned long long)tacc[k]);
+    atomicAdd(a.timing + 11, (unsigned long long)it);
+  }
+#endif
+#pragma unroll
+  for (int m = 0; m < 6; m++) {
+    const uint32_t c = (uint32_t)(stat_acc >> (10 * m)) & 1023u;
+    if (c) atomicAdd(&s_misc[40 + m], c * BL);
   }
   bar_workers();
   if (tid < 6 && s_misc[40 + tid]) atomicAdd(a.result + 2 + tid, (unsigned long long)s_misc[40 + tid]);

@@ -32,6 +32,7 @@ struct EncodeArgs {
   unsigned long long *status;  // [n_frames] look-back words, zeroed before launch
   unsigned int *ticket;        // zeroed before launch
   unsigned long long *result;  // [0] total bytes, [1] overflow flag, [2..8) stats; zeroed before launch
+  unsigned long long *timing;  // 32 words, only written when built with -DX3_ENC_TIMING
   const uint16_t *crc_tables;  // kCrcTableEntries
 };
 

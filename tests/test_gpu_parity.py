@@ -319,3 +319,19 @@ def test_cpp_cli_round_trip(pkg, oracle, tmp_path):
     r = subprocess.run([exe, "-i", str(tmp_path / "bad.x3a"), "-o", str(tmp_path / "bad.wav")], capture_output=True, text=True)
     assert r.returncode == 1 and "FrameHeaderInvalidPayloadCRC" in r.stderr
     assert os.path.getsize(tmp_path / "bad.wav") == 44
+
+
+def test_encode_host_pipelined_chunks(pkg, dev, oracle):
+    """x3_encode_host streams large inputs through the device in chunks of whole frames (three CUDA streams);
+    the concatenated result must still be the reference's byte stream, and capacity errors must be reported."""
+    n = 3 * 2400 * 10000 + 4567          # several 48 MiB chunks and a short last frame
+    pcm = dev.synth(4, 0x58330004, 384000, 0, n).cpu().numpy()
+    ref, rstats = oracle.encode(pcm, threads=8)
+    got, stats = pkg.encoder.encode_array(pcm, pkg.x3.Parameters.default())
+    assert got.size == ref.size and np.array_equal(got, ref) and stats == rstats
+    lib = pkg._lib.lib()
+    ps = pkg.x3.Parameters.default().c_struct()
+    small = np.empty(ref.size - 100, dtype=np.uint8)
+    out_len = C.c_size_t()
+    rc = lib.x3_encode_host(pcm.ctypes.data, pcm.size, C.byref(ps), small.ctypes.data, small.size, C.byref(out_len), None)
+    assert rc == pkg.error.BYTEWRITER_INSUFFICIENT_MEMORY

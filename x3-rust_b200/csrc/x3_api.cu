@@ -2,8 +2,10 @@
 // entry point fails with X3_ERR_CUDA when no device is usable.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -268,6 +270,84 @@ int x3_read_frame_header(const uint8_t *b, size_t len, x3_frame_header *h) {
 // ------------------------------------------------------------------------------------------------
 // encode
 // ------------------------------------------------------------------------------------------------
+namespace {
+
+size_t encode_ws_bytes(unsigned long long nf) { return 128 + 8 * (size_t)nf + 256; }  // + optional phase timing words
+
+// per-thread resources of the pipelined host path (x3_encode_host)
+struct HostPipe {
+  int device = -1;
+  cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  int16_t *d_pcm[2] = {nullptr, nullptr};
+  uint8_t *d_out[2] = {nullptr, nullptr};
+  unsigned char *ws[2] = {nullptr, nullptr};
+  size_t cap_pcm[2] = {0, 0}, cap_out[2] = {0, 0}, cap_ws[2] = {0, 0}, cap_res = 0;
+  unsigned long long *h_res = nullptr;
+  void release() {
+    for (int b = 0; b < 2; b++) {
+      if (d_pcm[b]) cudaFree(d_pcm[b]);
+      if (d_out[b]) cudaFree(d_out[b]);
+      if (ws[b]) cudaFree(ws[b]);
+      if (ev_in[b]) cudaEventDestroy(ev_in[b]);
+      if (ev_cmp[b]) cudaEventDestroy(ev_cmp[b]);
+      if (ev_out[b]) cudaEventDestroy(ev_out[b]);
+      d_pcm[b] = nullptr; d_out[b] = nullptr; ws[b] = nullptr; ev_in[b] = ev_cmp[b] = ev_out[b] = nullptr;
+      cap_pcm[b] = cap_out[b] = cap_ws[b] = 0;
+    }
+    if (h_res) cudaFreeHost(h_res);
+    if (s_in) cudaStreamDestroy(s_in);
+    if (s_cmp) cudaStreamDestroy(s_cmp);
+    if (s_out) cudaStreamDestroy(s_out);
+    h_res = nullptr; cap_res = 0; s_in = s_cmp = s_out = nullptr;
+    cudaGetLastError();
+  }
+  ~HostPipe() {}  // left to process teardown: the CUDA context may already be gone when thread-locals die
+};
+thread_local HostPipe tl_pipe;
+
+// zero the workspace and launch the encode kernel for n_samples (> 0) on `st`; no synchronisation
+cudaError_t enqueue_encode(Derived d, DeviceState *ds, const int16_t *d_pcm, size_t n_samples, uint8_t *d_out, size_t out_cap,
+                           unsigned char *ws, cudaStream_t st, int *rc_out) {
+  *rc_out = X3_OK;
+  const unsigned long long nf = (n_samples + d.P.spf - 1) / d.P.spf;
+  cudaError_t e = cudaMemsetAsync(ws, 0, encode_ws_bytes(nf), st);
+  if (e != cudaSuccess) return e;
+  EncodeArgs a;
+  a.pcm = d_pcm;
+  a.n_samples = n_samples;
+  a.out = d_out;
+  a.out_cap = out_cap;
+  a.P = d.P;
+  a.n_frames = (uint32_t)nf;
+  a.max_blocks = d.max_blocks;
+  a.out_words_cap = d.out_words_cap;
+  a.result = reinterpret_cast<unsigned long long *>(ws);        // 8 words
+  a.ticket = reinterpret_cast<unsigned int *>(ws + 64);
+  a.status = reinterpret_cast<unsigned long long *>(ws + 128);
+  a.timing = reinterpret_cast<unsigned long long *>(ws + 128 + 8 * (size_t)nf);
+  a.crc_tables = ds->crc_dev;
+  // the fast kernel stages frames with 16-byte cp.async: it needs a 16-byte aligned base and frame size
+  if (d.fast && ((((uintptr_t)d_pcm) & 15u) != 0 || ((d.P.spf * 2u) & 15u) != 0)) {
+    d.fast = false;
+    d.smem = encode_smem_bytes(d.P, d.max_blocks, d.out_words_cap);
+    if (d.smem > kMaxDynSmem) { *rc_out = X3_ERR_UNSUPPORTED_PARAMS; return cudaSuccess; }
+  }
+  const int occ = encode_occupancy(d.fast, d.smem);
+  unsigned long long grid = (unsigned long long)ds->sms * (unsigned)occ;
+  if (d.fast) {  // CTA 0 is the scanner, the others encode
+    if (grid > nf + 1) grid = nf + 1;
+    if (grid < 2) grid = 2;
+  } else if (grid > nf) {
+    grid = nf;
+  }
+  e = launch_encode(a, d.fast, (int)grid, d.smem, st);
+  g_launches++;
+  return e;
+}
+
+}  // namespace
+
 int x3_encode_device(const int16_t *d_pcm, size_t n_samples, const x3_params *p, uint8_t *d_out, size_t out_cap,
                      size_t *out_len, x3_stats *stats, void *cuda_stream) {
   Derived d;
@@ -287,46 +367,14 @@ int x3_encode_device(const int16_t *d_pcm, size_t n_samples, const x3_params *p,
 
   const unsigned long long nf = (n_samples + d.P.spf - 1) / d.P.spf;
   if (nf > 0xfffffff0ull) return X3_ERR_UNSUPPORTED_PARAMS;
-  const size_t ws_bytes = 128 + 8 * (size_t)nf + 256;  // + 32 words of optional phase timing (X3_ENC_TIMING)
+  const size_t ws_bytes = encode_ws_bytes(nf);
   unsigned char *ws = nullptr;
   CU(cudaMallocAsync(&ws, ws_bytes, st));
-  cudaError_t e = cudaMemsetAsync(ws, 0, ws_bytes, st);
-  if (e != cudaSuccess) { cudaFreeAsync(ws, st); return cuda_fail(e, "cudaMemsetAsync"); }
-
-  EncodeArgs a;
-  a.pcm = d_pcm;
-  a.n_samples = n_samples;
-  a.out = d_out;
-  a.out_cap = out_cap;
-  a.P = d.P;
-  a.n_frames = (uint32_t)nf;
-  a.max_blocks = d.max_blocks;
-  a.out_words_cap = d.out_words_cap;
-  a.result = reinterpret_cast<unsigned long long *>(ws);        // 8 words
-  a.ticket = reinterpret_cast<unsigned int *>(ws + 64);
-  a.status = reinterpret_cast<unsigned long long *>(ws + 128);
-  a.timing = reinterpret_cast<unsigned long long *>(ws + 128 + 8 * (size_t)nf);
-  a.crc_tables = ds->crc_dev;
-
-  // the fast kernel stages frames with 16-byte cp.async: it needs a 16-byte aligned base and frame size
-  if (d.fast && ((((uintptr_t)d_pcm) & 15u) != 0 || ((d.P.spf * 2u) & 15u) != 0)) {
-    d.fast = false;
-    d.smem = encode_smem_bytes(d.P, d.max_blocks, d.out_words_cap);
-    if (d.smem > kMaxDynSmem) return X3_ERR_UNSUPPORTED_PARAMS;
-  }
-  const int occ = encode_occupancy(d.fast, d.smem);
-  unsigned long long grid = (unsigned long long)ds->sms * (unsigned)occ;
-  if (d.fast) {  // CTA 0 is the scanner, the others encode
-    if (grid > nf + 1) grid = nf + 1;
-    if (grid < 2) grid = 2;
-  } else if (grid > nf) {
-    grid = nf;
-  }
   Timer tm(st);
   tm.start();
-  e = launch_encode(a, d.fast, (int)grid, d.smem, st);
+  cudaError_t e = enqueue_encode(d, ds, d_pcm, n_samples, d_out, out_cap, ws, st, &rc);
   tm.stop();
-  g_launches++;
+  if (rc) { cudaFreeAsync(ws, st); return rc; }
   if (e == cudaSuccess) e = cudaMemcpyAsync(host_res, ws, 64, cudaMemcpyDeviceToHost, st);
 #ifdef X3_ENC_TIMING
   if (e == cudaSuccess) e = cudaMemcpyAsync(host_res + 16, ws + 128 + 8 * (size_t)nf, 256, cudaMemcpyDeviceToHost, st);
@@ -362,29 +410,124 @@ int x3_encode_host(const int16_t *pcm, size_t n_samples, const x3_params *p, uin
   *out_len = 0;
   if (stats) memset(stats, 0, sizeof *stats);
   if (n_samples == 0) return X3_OK;
-  cudaStream_t st = nullptr;
   DeviceState *ds;
   if ((rc = device_state(&ds))) return rc;
-  const size_t bound = x3_encode_bound(n_samples, p);
-  const size_t dcap = bound < out_cap ? bound : out_cap;  // never write more than the caller has room for
-  int16_t *d_pcm = nullptr;
-  uint8_t *d_out = nullptr;
-  CU(cudaMallocAsync(&d_pcm, n_samples * sizeof(int16_t), st));
-  cudaError_t e = cudaMallocAsync(&d_out, dcap ? dcap : 1, st);
-  if (e != cudaSuccess) { cudaFreeAsync(d_pcm, st); return cuda_fail(e, "cudaMallocAsync"); }
-  e = cudaMemcpyAsync(d_pcm, pcm, n_samples * sizeof(int16_t), cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) {
-    rc = x3_encode_device(d_pcm, n_samples, p, d_out, dcap, out_len, stats, st);
-    if (rc == X3_OK || rc == X3_ERR_BYTEWRITER_INSUFFICIENT_MEMORY) {
-      const size_t ncopy = rc == X3_OK ? *out_len : 0;
-      if (ncopy) e = cudaMemcpyAsync(out, d_out, ncopy, cudaMemcpyDeviceToHost, st);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  const unsigned long long nf = (n_samples + d.P.spf - 1) / d.P.spf;
+  if (nf > 0xfffffff0ull) return X3_ERR_UNSUPPORTED_PARAMS;
+
+  // Chunks of whole frames flow through three streams: H2D of chunk c+1, the kernel of chunk c and the D2H of chunk
+  // c-1 overlap (PCIe is full duplex).  Frames are independent, so a chunk's stream is simply appended.
+  unsigned long long chunk_mb = 48;
+  if (const char *env = getenv("X3_HOST_CHUNK_MB")) chunk_mb = std::max(1, atoi(env));
+  const unsigned long long chunk_frames = std::max<unsigned long long>(1, (chunk_mb << 20) / ((unsigned long long)d.P.spf * 2ull));
+  const unsigned long long nchunks = (nf + chunk_frames - 1) / chunk_frames;
+  const size_t chunk_samples = (size_t)chunk_frames * d.P.spf;
+  const size_t chunk_bound = x3_encode_bound(std::min(chunk_samples, n_samples), p);
+  if (nchunks <= 1) {
+    // small input: one H2D, one kernel, one D2H on the default stream (pool allocations, no extra streams)
+    cudaStream_t st = nullptr;
+    const size_t dcap = chunk_bound < out_cap ? chunk_bound : out_cap;  // never write more than the caller has room for
+    int16_t *dp = nullptr;
+    uint8_t *dout = nullptr;
+    CU(cudaMallocAsync(&dp, n_samples * sizeof(int16_t), st));
+    cudaError_t e1 = cudaMallocAsync(&dout, dcap ? dcap : 1, st);
+    if (e1 != cudaSuccess) { cudaFreeAsync(dp, st); return cuda_fail(e1, "cudaMallocAsync"); }
+    e1 = cudaMemcpyAsync(dp, pcm, n_samples * sizeof(int16_t), cudaMemcpyHostToDevice, st);
+    if (e1 == cudaSuccess) {
+      rc = x3_encode_device(dp, n_samples, p, dout, dcap, out_len, stats, st);
+      if (rc == X3_OK && *out_len) {
+        e1 = cudaMemcpyAsync(out, dout, *out_len, cudaMemcpyDeviceToHost, st);
+        if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(st);
+      }
+    }
+    cudaFreeAsync(dp, st);
+    cudaFreeAsync(dout, st);
+    if (e1 != cudaSuccess) return cuda_fail(e1, "x3_encode_host copies");
+    return rc;
+  }
+  // streams, events, device buffers and the pinned result words are cached per host thread and device and only
+  // grow; creating and destroying them per call costs more than the copies they overlap
+  HostPipe &hp = tl_pipe;
+  cudaError_t e = cudaSuccess;
+#define CUP(call) do { e = (call); if (e != cudaSuccess) { hp.release(); return cuda_fail(e, #call); } } while (0)
+  {
+    int dev = 0;
+    CUP(cudaGetDevice(&dev));
+    if (hp.device != dev) { hp.release(); hp.device = dev; }
+    if (!hp.s_in) {
+      CUP(cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
+      CUP(cudaStreamCreateWithFlags(&hp.s_cmp, cudaStreamNonBlocking));
+      CUP(cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking));
+      for (int b = 0; b < 2; b++) {
+        CUP(cudaEventCreateWithFlags(&hp.ev_in[b], cudaEventDisableTiming));
+        CUP(cudaEventCreateWithFlags(&hp.ev_cmp[b], cudaEventDisableTiming));
+        CUP(cudaEventCreateWithFlags(&hp.ev_out[b], cudaEventDisableTiming));
+      }
+    }
+    const size_t need_pcm = std::min(chunk_samples, n_samples) * sizeof(int16_t);
+    const size_t need_out = chunk_bound ? chunk_bound : 1;
+    const size_t need_ws = encode_ws_bytes(std::min(chunk_frames, nf));
+    for (int b = 0; b < 2; b++) {
+      if (hp.cap_pcm[b] < need_pcm) { if (hp.d_pcm[b]) cudaFree(hp.d_pcm[b]); hp.d_pcm[b] = nullptr; hp.cap_pcm[b] = 0; CUP(cudaMalloc(&hp.d_pcm[b], need_pcm)); hp.cap_pcm[b] = need_pcm; }
+      if (hp.cap_out[b] < need_out) { if (hp.d_out[b]) cudaFree(hp.d_out[b]); hp.d_out[b] = nullptr; hp.cap_out[b] = 0; CUP(cudaMalloc(&hp.d_out[b], need_out)); hp.cap_out[b] = need_out; }
+      if (hp.cap_ws[b] < need_ws) { if (hp.ws[b]) cudaFree(hp.ws[b]); hp.ws[b] = nullptr; hp.cap_ws[b] = 0; CUP(cudaMalloc(&hp.ws[b], need_ws)); hp.cap_ws[b] = need_ws; }
+    }
+    if (hp.cap_res < (size_t)nchunks * 64) {
+      if (hp.h_res) cudaFreeHost(hp.h_res);
+      hp.h_res = nullptr; hp.cap_res = 0;
+      CUP(cudaMallocHost(&hp.h_res, (size_t)nchunks * 64));
+      hp.cap_res = (size_t)nchunks * 64;
     }
   }
-  cudaFreeAsync(d_pcm, st);
-  cudaFreeAsync(d_out, st);
-  if (e != cudaSuccess) return cuda_fail(e, "x3_encode_host copies");
-  return rc;
+  cudaStream_t s_in = hp.s_in, s_cmp = hp.s_cmp, s_out = hp.s_out;
+  cudaEvent_t *ev_in = hp.ev_in, *ev_cmp = hp.ev_cmp, *ev_out = hp.ev_out;
+  int16_t **d_pcm = hp.d_pcm;
+  uint8_t **d_out = hp.d_out;
+  unsigned char **ws = hp.ws;
+  unsigned long long *h_res = hp.h_res;
+  auto cleanup = [&]() {};
+
+  size_t off = 0;
+  bool overflow = false;
+  unsigned long long st6[6] = {0, 0, 0, 0, 0, 0};
+  // D2H of a finished chunk (its size is known only after its kernel): waits for the kernel, then queues the copy
+  auto finish = [&](unsigned long long c) -> cudaError_t {
+    const int b = (int)(c & 1);
+    cudaError_t ee = cudaEventSynchronize(ev_cmp[b]);
+    if (ee != cudaSuccess) return ee;
+    const unsigned long long *r = h_res + c * 8;
+    for (int k = 0; k < 6; k++) st6[k] += r[2 + k];
+    const size_t len = (size_t)r[0];
+    if (r[1] || off + len > out_cap) { overflow = true; off += len; return cudaEventRecord(ev_out[b], s_out); }
+    if (len) ee = cudaMemcpyAsync(out + off, d_out[b], len, cudaMemcpyDeviceToHost, s_out);
+    off += len;
+    if (ee == cudaSuccess) ee = cudaEventRecord(ev_out[b], s_out);
+    return ee;
+  };
+  for (unsigned long long c = 0; c < nchunks; c++) {
+    const int b = (int)(c & 1);
+    const size_t s0 = (size_t)c * chunk_samples;
+    const size_t ns = std::min(chunk_samples, n_samples - s0);
+    if (c >= 2) CUP(cudaStreamWaitEvent(s_in, ev_cmp[b], 0));   // d_pcm[b] is free once chunk c-2 was encoded
+    CUP(cudaMemcpyAsync(d_pcm[b], pcm + s0, ns * sizeof(int16_t), cudaMemcpyHostToDevice, s_in));
+    CUP(cudaEventRecord(ev_in[b], s_in));
+    CUP(cudaStreamWaitEvent(s_cmp, ev_in[b], 0));
+    if (c >= 2) CUP(cudaStreamWaitEvent(s_cmp, ev_out[b], 0));  // d_out[b] is free once chunk c-2 was copied out
+    int erc = X3_OK;
+    CUP(enqueue_encode(d, ds, d_pcm[b], ns, d_out[b], chunk_bound, ws[b], s_cmp, &erc));
+    if (erc) { cudaStreamSynchronize(s_in); cudaStreamSynchronize(s_cmp); cudaStreamSynchronize(s_out); return erc; }
+    CUP(cudaMemcpyAsync(h_res + c * 8, ws[b], 64, cudaMemcpyDeviceToHost, s_cmp));
+    CUP(cudaEventRecord(ev_cmp[b], s_cmp));
+    if (c >= 1) CUP(finish(c - 1));
+  }
+  CUP(finish(nchunks - 1));
+  CUP(cudaStreamSynchronize(s_out));
+#undef CUP
+  cleanup();
+  *out_len = off;
+  if (stats)
+    for (int k = 0; k < 6; k++) stats->samples_by_mode[k] = st6[k];
+  return overflow ? X3_ERR_BYTEWRITER_INSUFFICIENT_MEMORY : X3_OK;
 }
 
 int x3_encode_frame_host(const int16_t *pcm, size_t n_samples, const x3_params *p, uint8_t *out, size_t out_cap,

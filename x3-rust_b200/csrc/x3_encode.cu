@@ -473,7 +473,6 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
   uint16_t *s_crcT = reinterpret_cast<uint16_t *>(p);             p += kCrcTableEntries * 2;
   uint32_t *s_first = reinterpret_cast<uint32_t *>(p);            p += 512 * 4;
   uint32_t *s_V = reinterpret_cast<uint32_t *>(p);                p += NB * kMaxSlices * 4;
-  unsigned char *s_stat = p;                                       p += NB * 512;  // per block: stats index, 7 = none
   uint32_t *s_misc = reinterpret_cast<uint32_t *>(p);
   // s_misc: [0..16) warp totals, [32] next ticket, [40..46) stats of short blocks,
   //         per parity q at [48+8q ..): +0 frame, +1 samples, +2 payload_len, +4,+5 byte offset, +6 fits
@@ -790,7 +789,7 @@ size_t encode_smem_bytes(const CodecParams &P, uint32_t max_blocks, uint32_t out
 size_t encode_fast_smem_bytes(const CodecParams &P, uint32_t out_words_cap) {
   const uint32_t in_bytes = (2u * (P.spf + 8u) + 15u) & ~15u;
   const uint32_t img_bytes = (4u * (out_words_cap + 8u) + 15u) & ~15u;
-  return (size_t)in_bytes + NB * img_bytes + kCrcTableEntries * 2 + 512u * 4u + NB * kMaxSlices * 4u + NB * 512u + 96u * 4u;
+  return (size_t)in_bytes + NB * img_bytes + kCrcTableEntries * 2 + 512u * 4u + NB * kMaxSlices * 4u + 96u * 4u;
 }
 
 cudaError_t launch_encode(const EncodeArgs &a, bool fast, int grid, size_t smem, cudaStream_t stream) {

@@ -18,7 +18,7 @@ using namespace x3;
 
 namespace {
 constexpr int NT = 512;
-uint16_t g_T[kCrcTableEntries];
+uint16_t g_T[kCrcBankEntries2];
 bool g_T_ready = false;
 const uint16_t *T() {
   if (!g_T_ready) { build_crc_bank(g_T); g_T_ready = true; }
@@ -59,7 +59,7 @@ uint32_t crc_chunked(const uint32_t *words_img, uint32_t payload_len) {
 
 // CRC as the fast encode kernel does it: per-warp slices of 32 chunks (shuffle tree), then Horner over slices
 uint32_t crc_sliced(const uint32_t *words_img, uint32_t payload_len) {
-  const uint16_t *t = T();
+  const uint16_t *t = T(), *t2 = T() + kCrcTableEntries;
   const uint32_t m = payload_len >> 4, nslices = (m + 31u) >> 5;
   std::vector<uint32_t> V(nslices + 1);
   for (uint32_t j = 0; j < nslices; j++) {
@@ -69,17 +69,21 @@ uint32_t crc_sliced(const uint32_t *words_img, uint32_t payload_len) {
       h[lane] = 0;
       if (e < m) {
         const uint32_t c = m - 1u - e;
-        uint32_t s = c == 0 ? 0xffffu : 0u;
-        for (int w = 0; w < 4; w++) s = crc16_word(t, s, bswap32(words_img[4 * c + w]));
+        uint32_t s = c == 0 ? 0xffffu : 0u;  // byte-swapped state form, swapped table bank, words as they lie
+        for (int w = 0; w < 4; w++) s = crc16_word_sw(t2, s, words_img[4 * c + w]);
         h[lane] = s;
       }
     }
     for (int k = 0; k < 5; k++) {
       uint32_t o[32];
       for (int lane = 0; lane < 32; lane++) o[lane] = lane + (1 << k) < 32 ? h[lane + (1 << k)] : h[lane];
-      for (int lane = 0; lane < 32; lane++) h[lane] ^= crc16_mulc(t, 6 + 2 * k, o[lane]);
+      for (int lane = 0; lane < 32; lane++) {
+        const uint32_t x = o[lane] | 0xabcd0000u;  // bits above 15 must be ignored
+        h[lane] ^= k == 0 ? crc16_mulc_sw<6>(t2, x) : k == 1 ? crc16_mulc_sw<8>(t2, x) : k == 2 ? crc16_mulc_sw<10>(t2, x)
+                 : k == 3 ? crc16_mulc_sw<12>(t2, x) : crc16_mulc_sw<14>(t2, x);
+      }
     }
-    V[j] = h[0];
+    V[j] = bswap16(h[0]);
   }
   uint32_t s = 0;
   for (int j = (int)nslices - 1; j >= 0; j--) s = crc16_mulc(t, 4, s) ^ V[j];
@@ -113,7 +117,7 @@ size_t sim_encode_frame_fast(const int16_t *pcm, uint32_t n, const CodecParams &
     t.mode.kind = kRice; t.mode.k = 0; t.mode.hdr = 0; t.mode.stat = 0;
     t.nbits = 0; t.use_fast = false;
     if (t.active) {
-      if (t.len >= BL - 1) { t.use_fast = true; t.mode = block_measure_fast(s_in.data(), t.start, t.len, t.fb, t.nbits); }
+      if (t.len >= BL - 1) { t.use_fast = true; t.mode = block_measure_fast(s_in.data(), t.start, t.len, t.fb, t.nbits, -1); }
       else if (t.len > 0) t.mode = block_measure_generic(s_in.data(), t.start, t.len, P, t.nbits);
       if (b == 0) t.nbits += 16;
       if (t.len > 0) stats[t.mode.stat] += t.len;

@@ -36,7 +36,7 @@ int cuda_fail(cudaError_t e, const char *what) {
   } while (0)
 
 // ---- CRC table bank (layout in x3_common.cuh) -------------------------------------------------
-uint16_t g_crc_host[kCrcTableEntries];
+uint16_t g_crc_host[kCrcBankEntries2];
 std::once_flag g_crc_once;
 
 void build_crc_host() { build_crc_bank(g_crc_host); }
@@ -62,8 +62,8 @@ int device_state(DeviceState **out) {
   if (!d.crc_dev) {
     CU(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
     uint16_t *p = nullptr;
-    CU(cudaMalloc(&p, sizeof(uint16_t) * kCrcTableEntries));
-    CU(cudaMemcpy(p, crc_host(), sizeof(uint16_t) * kCrcTableEntries, cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&p, sizeof(uint16_t) * kCrcBankEntries2));
+    CU(cudaMemcpy(p, crc_host(), sizeof(uint16_t) * kCrcBankEntries2, cudaMemcpyHostToDevice));
     d.crc_dev = p;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
@@ -327,6 +327,7 @@ cudaError_t enqueue_encode(Derived d, DeviceState *ds, const int16_t *d_pcm, siz
   a.status = reinterpret_cast<unsigned long long *>(ws + 128);
   a.timing = reinterpret_cast<unsigned long long *>(ws + 128 + 8 * (size_t)nf);
   a.crc_tables = ds->crc_dev;
+  a.neg_one = -1;
   // the fast kernel stages frames with 16-byte cp.async: it needs a 16-byte aligned base and frame size
   if (d.fast && ((((uintptr_t)d_pcm) & 15u) != 0 || ((d.P.spf * 2u) & 15u) != 0)) {
     d.fast = false;

@@ -113,6 +113,9 @@ X3_HD int32_t unfold(uint32_t i) { return (int32_t)(i >> 1) ^ -(int32_t)(i & 1u)
 //   [6..16)  multiply by x^(128*2^k), k = 0..4 (lo, hi)    (warp tree combine)
 constexpr int kCrcTables = 16;
 constexpr int kCrcTableEntries = kCrcTables * 256;
+// A second bank of the same 16 tables with every entry byte-swapped follows the first one in device memory; the
+// fast encoder uses it (crc16_word_sw / crc16_mulc_sw below).
+constexpr int kCrcBankEntries2 = 2 * kCrcTableEntries;
 
 // one 32-bit big-endian word (first stream byte in bits 31..24) through the CRC state
 X3_HD uint32_t crc16_word(const uint16_t *T, uint32_t s, uint32_t w) {
@@ -144,6 +147,42 @@ X3_HD uint32_t crc16_half_alu(uint32_t s, uint32_t h) { return crc16_mulx16((s ^
 X3_HD uint32_t crc16_mulc(const uint16_t *T, int t, uint32_t s) {
   return (uint32_t)T[t * 256 + (s & 0xff)] ^ (uint32_t)T[(t + 1) * 256 + ((s >> 8) & 0xff)];
 }
+
+// ---- "swapped" form: the CRC state is kept byte-swapped (s_sw = bswap16(s)) and data words are taken as they lie in
+// memory (little-endian load of stream bytes), with the byte-swapped table bank T2.  No bswap per word, and on the
+// device the table addresses come from IDP.4A (byte * 2 + table base in one FMA-pipe instruction) instead of
+// shift/mask pairs on the ALU pipe, which is the encoder's bottleneck.
+#if defined(__CUDA_ARCH__)
+template <int BYTE_OFF>
+__device__ __forceinline__ uint32_t lds_u16_off(uint32_t addr) {
+  uint32_t r;
+  asm("ld.shared.u16 %0, [%1+%2];" : "=r"(r) : "r"(addr), "n"(BYTE_OFF));
+  return r;
+}
+#endif
+// stream bytes b0..b3 = bits 0..7, 8..15, 16..23, 24..31 of w_le
+X3_HD uint32_t crc16_word_sw(const uint16_t *T2, uint32_t s_sw, uint32_t w_le) {
+  const uint32_t v = s_sw ^ w_le;
+#if defined(__CUDA_ARCH__)
+  const uint32_t tb = (uint32_t)__cvta_generic_to_shared(T2);
+  return lds_u16_off<1536>(__dp4a(v, 0x00000002u, tb)) ^ lds_u16_off<1024>(__dp4a(v, 0x00000200u, tb)) ^
+         lds_u16_off<512>(__dp4a(v, 0x00020000u, tb)) ^ lds_u16_off<0>(__dp4a(v, 0x02000000u, tb));
+#else
+  return (uint32_t)T2[768 + (v & 0xff)] ^ (uint32_t)T2[512 + ((v >> 8) & 0xff)] ^
+         (uint32_t)T2[256 + ((v >> 16) & 0xff)] ^ (uint32_t)T2[v >> 24];
+#endif
+}
+// multiply a swapped 16-bit state (bits above 15 are ignored) by the constant of table pair TBL
+template <int TBL>
+X3_HD uint32_t crc16_mulc_sw(const uint16_t *T2, uint32_t s_sw) {
+#if defined(__CUDA_ARCH__)
+  const uint32_t tb = (uint32_t)__cvta_generic_to_shared(T2);
+  return lds_u16_off<TBL * 512>(__dp4a(s_sw, 0x00000200u, tb)) ^ lds_u16_off<(TBL + 1) * 512>(__dp4a(s_sw, 0x00000002u, tb));
+#else
+  return (uint32_t)T2[TBL * 256 + ((s_sw >> 8) & 0xff)] ^ (uint32_t)T2[(TBL + 1) * 256 + (s_sw & 0xff)];
+#endif
+}
+X3_HD uint32_t bswap16(uint32_t s) { return ((s & 0xffu) << 8) | ((s >> 8) & 0xffu); }
 
 // frame header bytes 0..16 -> header CRC (encoder.rs:153); words are big-endian images of the bytes
 X3_HD uint32_t header_crc(const uint16_t *T, uint32_t id, uint32_t num_samples, uint32_t payload_len) {

@@ -21,7 +21,7 @@ inline uint16_t crc_xpow(unsigned n) {  // x^n mod P
   for (unsigned i = 0; i < n; i++) s = crc_shift1(s);
   return s;
 }
-inline void build_crc_bank(uint16_t *T /*[kCrcTableEntries]*/) {
+inline void build_crc_bank(uint16_t *T /*[kCrcBankEntries2]*/) {
   for (int b = 0; b < 256; b++) {
     uint16_t c = (uint16_t)(b << 8);
     for (int j = 0; j < 8; j++) c = crc_shift1(c);  // b * x^16, the table of crc.rs:22-42
@@ -38,6 +38,7 @@ inline void build_crc_bank(uint16_t *T /*[kCrcTableEntries]*/) {
   };
   fill_mul(4, crc_xpow(4096));                                    // 32 chunks of 16 bytes
   for (int k = 0; k < 5; k++) fill_mul(6 + 2 * k, crc_xpow(128u << k));  // 2^k chunks of 16 bytes
+  for (int i = 0; i < kCrcTableEntries; i++) T[kCrcTableEntries + i] = (uint16_t)((T[i] << 8) | (T[i] >> 8));  // swapped bank
 }
 
 }  // namespace x3

@@ -192,20 +192,63 @@ X3_HD bool params_are_default(const CodecParams &P) {
          P.thresholds[1] == 8 && P.thresholds[2] == 20;
 }
 
-// reads s[start-1 .. start+19]; sample 19 is ignored (u=0) when len == 19
-X3_HD BlockMode block_measure_fast(const int16_t *s, uint32_t start, uint32_t len, FastBlock &fb, uint32_t &nbits) {
-  int32_t prev = s[start - 1];
-  fb.pred = prev;
+// d + a.lo16 * b.byte0 + a.hi16 * b.byte1 (all signed): IDP.2A on sm_100a, which issues on the FMA pipe.  The
+// encoder is bound by the ALU pipe (LOP3/SHF/PRMT/ISETP), so sample extraction and differencing go through here.
+X3_HD int32_t dp2a_s16s8(uint32_t a, uint32_t b, int32_t c) {
+#if defined(__CUDA_ARCH__)
+  return __dp2a_lo((int)a, (int)b, c);
+#else
+  return c + (int32_t)(int16_t)(a & 0xffffu) * (int32_t)(int8_t)(b & 0xffu) +
+         (int32_t)(int16_t)(a >> 16) * (int32_t)(int8_t)((b >> 8) & 0xffu);
+#endif
+}
+X3_HD uint32_t mulhi_add(uint32_t a, uint32_t b, uint32_t c) {  // IMAD.HI.U32: hi32(a*b) + c
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b) + c;
+#else
+  return (uint32_t)(((uint64_t)a * b) >> 32) + c;
+#endif
+}
+
+// Reads s[start-1 .. start+20] as eleven aligned 32-bit words (start is odd: 1 + 20*b); sample 19 is ignored
+// (u = 0) when len == 19.  `neg1` is -1 in a register the compiler cannot see through (a kernel argument), so that
+// ~p is computed as p * neg1 + neg1 on the FMA pipe.
+// With p = 2d: fold(d) = max(p, ~p)  (p >= 0: 2d > -2d-1; p < 0: -2d-1 > 2d), one IDP/IMAD pair + one VIMNMX.
+X3_HD BlockMode block_measure_fast(const int16_t *s, uint32_t start, uint32_t len, FastBlock &fb, uint32_t &nbits,
+                                   int32_t neg1) {
+  uint32_t W[kFastBL / 2 + 1];
+#if defined(__CUDA_ARCH__)
+  {
+    const uint2 *w2 = reinterpret_cast<const uint2 *>(s + (start - 1));  // byte offset 40*b: 8-byte aligned
+#pragma unroll
+    for (int j = 0; j < kFastBL / 4; j++) {
+      const uint2 v = w2[j];
+      W[2 * j] = v.x;
+      W[2 * j + 1] = v.y;
+    }
+    W[kFastBL / 2] = reinterpret_cast<const uint32_t *>(s + (start - 1))[kFastBL / 2];
+  }
+#else
+  for (int j = 0; j <= kFastBL / 2; j++)
+    W[j] = (uint32_t)(uint16_t)s[start - 1 + 2 * j] | ((uint32_t)(uint16_t)s[start + 2 * j] << 16);
+#endif
+  constexpr uint32_t kHiMinusLo = 0x02feu;  // byte0 = -2, byte1 = +2
+  constexpr uint32_t kMinusHi = 0xfe00u;    // byte0 =  0, byte1 = -2
+  constexpr uint32_t kPlusLo = 0x0002u;     // byte0 = +2, byte1 =  0
+  fb.pred = dp2a_s16s8(W[0], 0x0001u, 0);   // s[start-1]
   uint32_t maxu = 0, sumu = 0;
 #pragma unroll
-  for (int i = 0; i < kFastBL; i++) {
-    int32_t x = s[start + i];
-    uint32_t u = fold(x - prev);
-    if (i == kFastBL - 1 && len != (uint32_t)kFastBL) u = 0;
-    prev = x;
-    fb.u[i] = u;
-    maxu = u > maxu ? u : maxu;
-    sumu += u;
+  for (int j = 0; j < kFastBL / 2; j++) {
+    const int32_t p0 = dp2a_s16s8(W[j], kHiMinusLo, 0);                                   // 2*(s[2j+1] - s[2j])
+    const int32_t p1 = dp2a_s16s8(W[j + 1], kPlusLo, dp2a_s16s8(W[j], kMinusHi, 0));      // 2*(s[2j+2] - s[2j+1])
+    const int32_t n0 = p0 * neg1 + neg1, n1 = p1 * neg1 + neg1;                           // ~p
+    uint32_t u0 = (uint32_t)(p0 > n0 ? p0 : n0), u1 = (uint32_t)(p1 > n1 ? p1 : n1);
+    if (j == kFastBL / 2 - 1 && len != (uint32_t)kFastBL) u1 = 0;
+    fb.u[2 * j] = u0;
+    fb.u[2 * j + 1] = u1;
+    const uint32_t m01 = u0 > u1 ? u0 : u1;
+    maxu = m01 > maxu ? m01 : maxu;
+    sumu += u0 + u1;
   }
   const uint32_t max_abs = (maxu + 1u) >> 1;
   BlockMode m;
@@ -217,9 +260,11 @@ X3_HD BlockMode block_measure_fast(const int16_t *s, uint32_t start, uint32_t le
     m.hdr = ftype + 1;
     m.stat = m.k;
     if (m.k) {
+      // sum of u >> k as hi32(u * 2^(32-k)) accumulated by IMAD.HI (FMA pipe)
+      const uint32_t mult = 0x80000000u >> (m.k - 1u);
       sum_q = 0;
 #pragma unroll
-      for (int i = 0; i < kFastBL; i++) sum_q += fb.u[i] >> m.k;
+      for (int i = 0; i < kFastBL; i++) sum_q = mulhi_add(fb.u[i], mult, sum_q);
     }
   } else {
     uint32_t nb = 32u - clz32(max_abs);

@@ -310,24 +310,45 @@ constexpr int NTF = kEncFastThreads;      // 544
 constexpr int NWW = 16;                   // worker warps
 constexpr int kMaxSlices = 64;
 constexpr uint32_t kNoFrame = 0xffffffffu;
+constexpr uint32_t kStdSpf = 10000, kStdOwc = 5096;  // Parameters::default(): 20 x 500 samples, 16 + 500*326 bits
 constexpr uint32_t NB = 3;                // frame images in flight per CTA (slack for the look-back: NB-1 frames)
 
-// lean frame stager for the fast kernel: the API guarantees a 16-byte aligned PCM base and frame size there, so
-// it is two or three cp.async per worker thread with 32-bit index math (the generic stager costs ~100
-// instructions per thread and frame)
-__device__ __forceinline__ void stage_frame_fast(const int16_t *pcm, unsigned long long s0, uint32_t n, int16_t *s_in, int tid) {
-  const char *g = reinterpret_cast<const char *>(pcm + s0) + tid * 16;
-  uint32_t sa = (uint32_t)__cvta_generic_to_shared(s_in) + (uint32_t)tid * 16u;
-  const uint32_t chunks = n >> 3;  // 8 samples = 16 bytes
-  for (uint32_t c = tid; c < chunks; c += 512u) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(g) : "memory");
-    sa += 512u * 16u;
-    g += 512 * 16;
+// Frame stager of the fast kernel: ONE bulk async copy (TMA, cp.async.bulk) of the frame's PCM into shared memory,
+// issued by a single thread and completed on an mbarrier that every worker waits on.  The API guarantees a 16-byte
+// aligned PCM base and frame size for this kernel.  (Per-thread 16-byte cp.async cost ~30 instructions per thread
+// and frame in address arithmetic.)  Samples beyond the last whole 16 bytes -- only in the stream's last frame --
+// are copied by stage_tail_fast with plain loads.
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(mbar), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "X3_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra X3_MBAR_DONE;\n"
+      "bra X3_MBAR_WAIT;\n"
+      "X3_MBAR_DONE:\n"
+      "}\n" ::"r"(mbar), "r"(parity) : "memory");
+}
+// called by one thread
+__device__ __forceinline__ void stage_frame_bulk(const int16_t *pcm, unsigned long long s0, uint32_t n, int16_t *s_in, uint32_t mbar) {
+  const uint32_t bytes = (n >> 3) << 4;
+  if (bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(s_in)),
+                 "l"(pcm + s0), "r"(bytes), "r"(mbar)
+                 : "memory");
+  } else {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(mbar) : "memory");
   }
-  if (n & 7u) {  // only the stream's last frame
-    for (uint32_t i = (chunks << 3) + tid; i < n; i += 512u) s_in[i] = __ldg(pcm + s0 + i);
-  }
-  cp_async_commit();
+}
+// called by all 512 workers; a barrier must follow before s_in is read
+__device__ __forceinline__ void stage_tail_fast(const int16_t *pcm, unsigned long long s0, uint32_t n, int16_t *s_in, int tid) {
+  for (uint32_t i = (n & ~7u) + tid; i < n; i += 512u) s_in[i] = __ldg(pcm + s0 + i);
 }
 
 #ifdef X3_ENC_TIMING
@@ -337,35 +358,12 @@ __device__ __forceinline__ void stage_frame_fast(const int16_t *pcm, unsigned lo
 #endif
 
 __device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 1, 512;\n" ::: "memory"); }
-// barrier ids are immediates so that ptxas reserves exactly the eight barriers used (not all sixteen)
-__device__ __forceinline__ void bar_sync_all(int id) {
-  switch (id) {
-    case 2: asm volatile("bar.sync 2, 544;\n" ::: "memory"); break;
-    case 3: asm volatile("bar.sync 3, 544;\n" ::: "memory"); break;
-    case 4: asm volatile("bar.sync 4, 544;\n" ::: "memory"); break;
-    case 5: asm volatile("bar.sync 5, 544;\n" ::: "memory"); break;
-    case 6: asm volatile("bar.sync 6, 544;\n" ::: "memory"); break;
-    case 7: asm volatile("bar.sync 7, 544;\n" ::: "memory"); break;
-    case 8: asm volatile("bar.sync 8, 544;\n" ::: "memory"); break;
-    case 9: asm volatile("bar.sync 9, 544;\n" ::: "memory"); break;
-    default: asm volatile("bar.sync 10, 544;\n" ::: "memory"); break;
-  }
-}
-__device__ __forceinline__ void bar_arrive_all(int id) {
-  // bar.arrive orders this thread's prior shared-memory writes for the threads that bar.sync on the same barrier
-  // (the PTX producer/consumer idiom); an explicit MEMBAR here cost ~600 cycles per frame
-  switch (id) {
-    case 2: asm volatile("bar.arrive 2, 544;\n" ::: "memory"); break;
-    case 3: asm volatile("bar.arrive 3, 544;\n" ::: "memory"); break;
-    case 4: asm volatile("bar.arrive 4, 544;\n" ::: "memory"); break;
-    case 5: asm volatile("bar.arrive 5, 544;\n" ::: "memory"); break;
-    case 6: asm volatile("bar.arrive 6, 544;\n" ::: "memory"); break;
-    case 7: asm volatile("bar.arrive 7, 544;\n" ::: "memory"); break;
-    case 8: asm volatile("bar.arrive 8, 544;\n" ::: "memory"); break;
-    case 9: asm volatile("bar.arrive 9, 544;\n" ::: "memory"); break;
-    default: asm volatile("bar.arrive 10, 544;\n" ::: "memory"); break;
-  }
-}
+// the barrier id is a register operand: ptxas then reserves all 16 barriers of the CTA, which still allows
+// 4 CTAs per SM (2 are resident); a switch over immediate ids cost ~30 instructions per frame and thread
+__device__ __forceinline__ void bar_sync_all(uint32_t id) { asm volatile("bar.sync %0, 544;\n" ::"r"(id) : "memory"); }
+// bar.arrive orders this thread's prior shared-memory writes for the threads that bar.sync on the same barrier
+// (the PTX producer/consumer idiom); an explicit MEMBAR here cost ~600 cycles per frame
+__device__ __forceinline__ void bar_arrive_all(uint32_t id) { asm volatile("bar.arrive %0, 544;\n" ::"r"(id) : "memory"); }
 constexpr int kBarSize = 2, kBarCrc = 5, kBarOff = 8;  // + buffer index (0..NB-1)
 
 // payload image (16-byte aligned in shared memory) -> dst (2-byte aligned global address), 512 worker threads.
@@ -458,22 +456,29 @@ __device__ __forceinline__ void scanner_role(const EncodeArgs &a) {
   if (lane == 0) a.result[0] = running;  // total stream length
 }
 
-__global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const EncodeArgs a) {
+// SPF / OWC != 0: samples per frame and image words are compile-time constants (Parameters::default(), 500 blocks
+// per frame), which turns all shared-memory address arithmetic into immediates; 0 = take them from the arguments.
+template <uint32_t SPF, uint32_t OWC>
+__global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const __grid_constant__ EncodeArgs a) {
   if (blockIdx.x == 0) {
     scanner_role(a);
     return;
   }
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const uint32_t in_bytes = (2u * (a.P.spf + 8u) + 15u) & ~15u;
-  const uint32_t img_bytes = (4u * (a.out_words_cap + 8u) + 15u) & ~15u;
+  const uint32_t spf = SPF ? SPF : a.P.spf;
+  const uint32_t owc = OWC ? OWC : a.out_words_cap;
+  const uint32_t in_bytes = (2u * (spf + 8u) + 15u) & ~15u;
+  const uint32_t img_bytes = (4u * (owc + 8u) + 15u) & ~15u;
   unsigned char *p = smem_raw;
   int16_t *s_in = reinterpret_cast<int16_t *>(p);                 p += in_bytes;
   uint32_t *s_img = reinterpret_cast<uint32_t *>(p);              p += NB * img_bytes;
   const uint32_t img_words = img_bytes >> 2;
-  uint16_t *s_crcT = reinterpret_cast<uint16_t *>(p);             p += kCrcTableEntries * 2;
+  uint16_t *s_crcT = reinterpret_cast<uint16_t *>(p);             p += kCrcBankEntries2 * 2;
+  const uint16_t *s_crcT2 = s_crcT + kCrcTableEntries;            // byte-swapped bank (worker CRC)
   uint32_t *s_first = reinterpret_cast<uint32_t *>(p);            p += 512 * 4;
   uint32_t *s_V = reinterpret_cast<uint32_t *>(p);                p += NB * kMaxSlices * 4;
   uint32_t *s_misc = reinterpret_cast<uint32_t *>(p);
+  const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(s_misc + 80);  // 8 bytes: the frame stager's mbarrier
   // s_misc: [0..16) warp totals, [32] next ticket, [40..46) stats of short blocks,
   //         per parity q at [48+8q ..): +0 frame, +1 samples, +2 payload_len, +4,+5 byte offset, +6 fits
 
@@ -481,8 +486,9 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
   const bool worker = wid < NWW;
   constexpr uint32_t BL = 20;
 
-  for (int i = tid; i < kCrcTableEntries; i += NTF) s_crcT[i] = a.crc_tables[i];
+  for (int i = tid; i < kCrcBankEntries2; i += NTF) s_crcT[i] = a.crc_tables[i];
   if (tid < 6) s_misc[40 + tid] = 0;
+  if (tid == 0) mbar_init(mbar, 1);
   __syncthreads();
   // Frames are handed out by an atomic ticket, LATE: a CTA draws its next frame only when it has finished packing
   // the current one, so that a ticketed frame publishes its size within about one measure phase.  (Drawing the
@@ -568,28 +574,27 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
   bar_workers();
   uint32_t f = s_misc[32];
   if (f < a.n_frames) {
-    const unsigned long long s00 = (unsigned long long)f * a.P.spf;
+    const unsigned long long s00 = (unsigned long long)f * spf;
     const unsigned long long r0 = a.n_samples - s00;
-    stage_frame_fast(a.pcm, s00, r0 < a.P.spf ? (uint32_t)r0 : a.P.spf, s_in, tid);
+    const uint32_t n0 = r0 < spf ? (uint32_t)r0 : spf;
+    if (tid == 0) stage_frame_bulk(a.pcm, s00, n0, s_in, mbar);
+    if (n0 & 7u) stage_tail_fast(a.pcm, s00, n0, s_in, tid);
   }
   uint32_t it = 0, par = 0;
   unsigned long long stat_acc = 0;
 #ifdef X3_ENC_TIMING
   long long tacc[12] = {0}, tlast = clock64();
 #endif
-  uint32_t hist_len[NB];  // payload lengths of the frames still held in the image ring
-#pragma unroll
-  for (uint32_t q = 0; q < NB; q++) hist_len[q] = 0;
 
   while (f != kNoFrame && f < a.n_frames) {
     uint32_t *s_words = s_img + par * img_words;
-    const unsigned long long s0 = (unsigned long long)f * a.P.spf;
+    const unsigned long long s0 = (unsigned long long)f * spf;
     const unsigned long long remn = a.n_samples - s0;
-    const uint32_t n = remn < a.P.spf ? (uint32_t)remn : a.P.spf;
+    const uint32_t n = remn < spf ? (uint32_t)remn : spf;
     const uint32_t nblk = n > 1 ? (n - 2u) / BL + 1u : 1u;  // <= 512
 
-    cp_async_wait_all();
-    bar_workers();  // (A) samples staged
+    if (n & 7u) bar_workers();  // the last frame's tail samples were stored by other threads
+    mbar_wait(mbar, it & 1u);   // (A) samples staged (bulk copy complete)
     X3_T(0)
 
     // ---- measure ----
@@ -606,7 +611,7 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
     if (active) {
       if (len >= BL - 1) {
         use_fast = true;
-        mode = block_measure_fast(s_in, start, len, fb, nbits);
+        mode = block_measure_fast(s_in, start, len, fb, nbits, a.neg_one);
       } else if (len > 0) {
         mode = block_measure_generic(s_in, start, len, a.P, nbits);  // short last block of the stream's last frame
       }
@@ -675,9 +680,11 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
     // stage the next frame now: s_in has been free since barrier (B), and the copy lands while the CRC and
     // the copy-out run
     if (f_next != kNoFrame) {
-      const unsigned long long s1 = (unsigned long long)f_next * a.P.spf;
+      const unsigned long long s1 = (unsigned long long)f_next * spf;
       const unsigned long long r1 = a.n_samples - s1;
-      stage_frame_fast(a.pcm, s1, r1 < a.P.spf ? (uint32_t)r1 : a.P.spf, s_in, tid);
+      const uint32_t n1 = r1 < spf ? (uint32_t)r1 : spf;
+      if (tid == 0) stage_frame_bulk(a.pcm, s1, n1, s_in, mbar);
+      if (n1 & 7u) stage_tail_fast(a.pcm, s1, n1, s_in, tid);
     }
 
     // ---- CRC of 16-byte chunks, combined per slice of 32 chunks by a shuffle tree.  Slice j covers the
@@ -692,36 +699,30 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
         if (e < m) {
           const uint32_t c = m - 1u - e;
           const uint4 q = reinterpret_cast<const uint4 *>(s_words)[c];
-          h = c == 0 ? 0xffffu : 0u;  // chunk 0 carries the CRC's initial value
-          h = crc16_word(s_crcT, h, bswap32(q.x));
-          h = crc16_word(s_crcT, h, bswap32(q.y));
-          h = crc16_word(s_crcT, h, bswap32(q.z));
-          h = crc16_word(s_crcT, h, bswap32(q.w));
+          h = c == 0 ? 0xffffu : 0u;  // chunk 0 carries the CRC's initial value (byte-swapped state form)
+          h = crc16_word_sw(s_crcT2, h, q.x);
+          h = crc16_word_sw(s_crcT2, h, q.y);
+          h = crc16_word_sw(s_crcT2, h, q.z);
+          h = crc16_word_sw(s_crcT2, h, q.w);
         }
-#pragma unroll
-        for (int k = 0; k < 5; k++) {
-          const uint32_t o = __shfl_down_sync(0xffffffffu, h, 1 << k);
-          h ^= crc16_mulc(s_crcT, 6 + 2 * k, o);
-        }
-        if (lane == 0) V[j] = h;
+        h ^= crc16_mulc_sw<6>(s_crcT2, __shfl_down_sync(0xffffffffu, h, 1));
+        h ^= crc16_mulc_sw<8>(s_crcT2, __shfl_down_sync(0xffffffffu, h, 2));
+        h ^= crc16_mulc_sw<10>(s_crcT2, __shfl_down_sync(0xffffffffu, h, 4));
+        h ^= crc16_mulc_sw<12>(s_crcT2, __shfl_down_sync(0xffffffffu, h, 8));
+        h ^= crc16_mulc_sw<14>(s_crcT2, __shfl_down_sync(0xffffffffu, h, 16));
+        if (lane == 0) V[j] = bswap16(h);
       }
     }
     bar_arrive_all(kBarCrc + par);  // -> control: slice CRCs and image complete
     X3_T(8)
 
     // ---- the oldest frame in the ring goes out now: its offset has had NB-1 frame times to arrive ----
-#pragma unroll
-    for (uint32_t q = 0; q < NB; q++)
-      if (q == par) hist_len[q] = payload_len;
     if (it >= NB - 1) {
       const uint32_t q = par + 1u == NB ? 0u : par + 1u;  // the buffer the next frame will reuse
       bar_sync_all(kBarOff + q);
       X3_T(9)
       const uint32_t *info = s_misc + 48 + 8 * q;
-      uint32_t L = 0;
-#pragma unroll
-      for (uint32_t k = 0; k < NB; k++)
-        if (k == q) L = hist_len[k];
+      const uint32_t L = info[2];  // payload length (stays valid until this buffer's next measure phase)
       if (info[6]) {
         const unsigned long long off = (unsigned long long)info[4] | ((unsigned long long)info[5] << 32);
         copy_payload_out(a.out + off + kFrameHeaderLen, s_img + q * img_words, L, tid);
@@ -747,10 +748,7 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const Encode
     for (uint32_t d = 0; d < pending; d++) {
       bar_sync_all(kBarOff + q);
       const uint32_t *info = s_misc + 48 + 8 * q;
-      uint32_t L = 0;
-#pragma unroll
-      for (uint32_t k = 0; k < NB; k++)
-        if (k == q) L = hist_len[k];
+      const uint32_t L = info[2];  // payload length (stays valid until this buffer's next measure phase)
       if (info[6]) {
         const unsigned long long off = (unsigned long long)info[4] | ((unsigned long long)info[5] << 32);
         copy_payload_out(a.out + off + kFrameHeaderLen, s_img + q * img_words, L, tid);
@@ -789,15 +787,17 @@ size_t encode_smem_bytes(const CodecParams &P, uint32_t max_blocks, uint32_t out
 size_t encode_fast_smem_bytes(const CodecParams &P, uint32_t out_words_cap) {
   const uint32_t in_bytes = (2u * (P.spf + 8u) + 15u) & ~15u;
   const uint32_t img_bytes = (4u * (out_words_cap + 8u) + 15u) & ~15u;
-  return (size_t)in_bytes + NB * img_bytes + kCrcTableEntries * 2 + 512u * 4u + NB * kMaxSlices * 4u + 96u * 4u;
+  return (size_t)in_bytes + NB * img_bytes + kCrcBankEntries2 * 2 + 512u * 4u + NB * kMaxSlices * 4u + 96u * 4u;
 }
 
 cudaError_t launch_encode(const EncodeArgs &a, bool fast, int grid, size_t smem, cudaStream_t stream) {
   cudaError_t e;
   if (fast) {
-    e = cudaFuncSetAttribute(encode_frames_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool std_frame = a.P.spf == kStdSpf && a.out_words_cap == kStdOwc;
+    auto kern = std_frame ? encode_frames_fast_kernel<kStdSpf, kStdOwc> : encode_frames_fast_kernel<0, 0>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    encode_frames_fast_kernel<<<grid, NTF, smem, stream>>>(a);
+    kern<<<grid, NTF, smem, stream>>>(a);
   } else {
     e = cudaFuncSetAttribute(encode_frames_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -810,8 +810,8 @@ int encode_occupancy(bool fast, size_t smem) {
   int nb = 0;
   cudaError_t e;
   if (fast) {
-    cudaFuncSetAttribute(encode_frames_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, encode_frames_fast_kernel, NTF, smem);
+    cudaFuncSetAttribute(encode_frames_fast_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, encode_frames_fast_kernel<0, 0>, NTF, smem);
   } else {
     cudaFuncSetAttribute(encode_frames_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, encode_frames_generic_kernel, NT, smem);

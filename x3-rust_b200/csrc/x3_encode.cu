@@ -501,12 +501,25 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const __grid
     long long tacc[12] = {0}, tlast = clock64();
     unsigned long long cframes = 0;
 #endif
-    for (uint32_t par = 0;; par = (par + 1u == NB ? 0u : par + 1u)) {
-      uint32_t *info = s_misc + 48 + 8 * par;
-      bar_sync_all(kBarSize + par);
+    // The control warp finishes frame i-1 (offset, CRC fold, header) when frame i's size signal arrives: by then
+    // frame i-1's size has been public for a whole frame time, so its prefix is normally there at the first poll,
+    // and the warp is never the serial bottleneck (poll + fold used to take as long as the workers take per frame).
+    bool have_prev = false;
+    uint32_t prev_par = 0;
+    for (uint32_t cur = 0;; cur = (cur + 1u == NB ? 0u : cur + 1u)) {
+      bar_sync_all(kBarSize + cur);
       X3_T(0)
+      const bool stop = s_misc[48 + 8 * cur] == kNoFrame;
+      const uint32_t par = prev_par;
+      const bool do_prev = have_prev;
+      have_prev = true;
+      prev_par = cur;
+      if (!do_prev) {
+        if (stop) break;
+        continue;
+      }
+      uint32_t *info = s_misc + 48 + 8 * par;
       const uint32_t f = info[0];
-      if (f == kNoFrame) break;
       const uint32_t n = info[1], payload_len = info[2];
       const uint32_t frame_bytes = (uint32_t)kFrameHeaderLen + payload_len;
       X3_T(1)
@@ -559,6 +572,7 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const __grid
 #ifdef X3_ENC_TIMING
       cframes++;
 #endif
+      if (stop) break;
     }
 #ifdef X3_ENC_TIMING
     if (lane == 0) {
@@ -741,8 +755,11 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const __grid
       stat_acc = 0;
     }
   }
-  // ---- drain: the frames still in the ring, oldest first, then tell the control warp to stop ----
+  // ---- drain: tell the control warp to stop (it finishes the last frame on this signal), then copy out the
+  // frames still in the ring, oldest first ----
   {
+    if (tid == 0) s_misc[48 + 8 * par] = kNoFrame;
+    bar_arrive_all(kBarSize + par);
     const uint32_t pending = it < NB - 1 ? it : NB - 1;
     uint32_t q = (par + NB - pending) % NB;
     for (uint32_t d = 0; d < pending; d++) {
@@ -755,8 +772,6 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const __grid
       }
       q = q + 1u == NB ? 0u : q + 1u;
     }
-    if (tid == 0) s_misc[48 + 8 * par] = kNoFrame;
-    bar_arrive_all(kBarSize + par);
   }
 #ifdef X3_ENC_TIMING
   if (tid == 0) {

@@ -275,7 +275,9 @@ int sim_decode_frame(const uint8_t *stream, size_t stream_len, size_t pos, uint3
     alignas(16) uint32_t stage[kStageWords];
     PlainBitReader rd;
     rd.init(pl, stream + stream_len);
-    r = decode_frame_fast(rd, payload_len, out, samples, stage, 1u);
+    static int16_t inv[kInvTabEntries];
+    for (int j = 0; j < kInvTabEntries; j++) inv[j] = inv_tab_entry(1 + j / kInvTabLen, j % kInvTabLen);
+    r = decode_frame_fast(rd, payload_len, out, samples, stage, 1u, inv);
     if (r == kDecOk) *used_fast = 1;
   }
   if (r == kDecRetryExact) r = decode_frame_exact(pl, payload_len, out, samples, P);

@@ -217,28 +217,68 @@ X3_HD bool frame_fast_eligible(uint32_t samples, uint32_t payload_len, uintptr_t
          (payload_addr & 1u) == 0u && (out_addr & 31u) == 0u;
 }
 
+// Inverse-fold table of the fast path: for ftype f = 1..3 (level = 1, 2, 8) entry [ip + kInvPad] of table f is
+// INV_RICE_CODE[ip - level] (x3.rs:200-204), the delta of the code whose tracked index is ip = r + level*z.
+// ip reaches 31*8+15 when the zero run is as long as the 32-bit peek can see, and is -level..-level+15 (as a
+// signed number) when the peek is all zeros (z = 0xffffffff): both land inside the table, the frame is then flagged
+// through max_ip and decoded again by the exact path.  One shared-memory load replaces five ALU instructions.
+constexpr int kInvPad = 8;
+constexpr int kInvTabLen = kInvPad + 264;          // per ftype
+constexpr int kInvTabEntries = 3 * kInvTabLen;
+X3_HD int16_t inv_tab_entry(int f /*1..3*/, int j /*0..kInvTabLen*/) {
+  const int level = f == 1 ? 1 : (f == 2 ? 2 : 8);
+  const int i = j - kInvPad - level;
+  return i < 0 ? (int16_t)0 : (int16_t)unfold((uint32_t)i);
+}
+
+// hi32(a * b) + c and a * b + c as single FMA-pipe instructions (IMAD.HI.U32 / IMAD): the decoder is bound by the
+// ALU pipe (shifts, logic, min/max), so the shift by a per-block amount is done as a multiply by a power of two.
+X3_HD uint32_t mad_hi_u32(uint32_t a, uint32_t b, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+  uint32_t d;
+  asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+#else
+  return (uint32_t)(((uint64_t)a * b) >> 32) + c;
+#endif
+}
+X3_HD uint32_t mad_lo_u32(uint32_t a, uint32_t b, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+  uint32_t d;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+#else
+  return a * b + c;
+#endif
+}
+X3_HD uint32_t pack_lo16(uint32_t lo, uint32_t hi) {  // (lo & 0xffff) | (hi << 16)
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(lo, hi, 0x5410);
+#else
+  return (lo & 0xffffu) | (hi << 16);
+#endif
+}
+
 // one Rice code at offset `cum` of the 64-bit window (decoder.rs:157-165 / :184-191 in closed form):
 //   z zeros, then nbk bits r of which the first is the terminator; index i = r + level*(z-1); delta = INV[i].
-// ip = i + level is what is tracked (one IMAD); delta = (i>>1) - (i odd ? i : 0).
-// An all-zero window gives z >= 32 (0xffffffff on the device): ip is then far beyond every inv_len.
-#define X3_RICE_SAMPLE()                                                              \
+// ip = i + level = r + level*z is what is tracked: r = (t << z) >> (32 - nbk) = hi32((t << z) * 2^nbk), so
+// ip = IMAD.HI(t << z, 2^nbk, IMAD(z, level, 0)); delta = tab[ip].
+// An all-zero window gives z = 0xffffffff on the device (32 on the host): t << z is 0, ip = -level (host: 32*level).
+#define X3_RICE_SAMPLE(ipv)                                                           \
   {                                                                                   \
     const uint32_t t = funnel_l(lo, hi, cum);                                         \
     const uint32_t z = clz_shift(t);                                                  \
-    const uint32_t r = shl_safe(t, z) >> (32u - nbk);                                 \
+    ipv = mad_hi_u32(shl_safe(t, z), pown, mad_lo_u32(z, level, 0u));                 \
     cum += z + nbk;                                                                   \
-    const uint32_t ip = z * (uint32_t)level + r;                                      \
-    max_ip = ip > max_ip ? ip : max_ip;                                               \
-    const uint32_t i = ip - (uint32_t)level;                                          \
-    lw += (int32_t)(i >> 1);                                                          \
-    if (i & 1u) lw -= (int32_t)i;                                                     \
+    lw += (int32_t)tab[(int32_t)ipv];                                                 \
   }
 
 // Decode one frame.  `stage` = this thread's staging area: 40 words, `ss` words apart.
 // Returns kDecOk or kDecRetryExact.
+// `inv_tab` = kInvTabEntries entries built with inv_tab_entry (shared memory on the device).
 template <class Reader>
 X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint32_t samples, uint32_t *stage,
-                            const uint32_t ss) {
+                            const uint32_t ss, const int16_t *inv_tab) {
   uint32_t hi, lo;
   rd.block_begin();
   rd.window(hi, lo);
@@ -261,28 +301,38 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
       // ---- Rice block: z zeros, then nbk bits of which the first is the terminator ----
       rd.advance(2);
       const uint32_t nbk = ftype == 1u ? 1u : (ftype == 2u ? 2u : 4u);          // decoder.rs:158,180
-      const int32_t level = ftype == 1u ? 1 : (ftype == 2u ? 2 : 8);            // 1<<nsubs of RICE1 / RICE3
-      const uint32_t inv_len = ftype == 1u ? 16u : (ftype == 2u ? 26u : 60u);   // x3.rs:214,222,250
-      uint32_t max_ip = 0, cum = 0, cmax = 0;
+      const uint32_t level = ftype == 1u ? 1u : (ftype == 2u ? 2u : 8u);        // 1<<nsubs of RICE1 / RICE3
+      const uint32_t pown = 1u << nbk;
+      const uint32_t ip_end = ftype == 1u ? 17u : (ftype == 2u ? 28u : 68u);    // inv_len + level (x3.rs:214,222,250)
+      const int16_t *tab = inv_tab + (ftype - 1u) * (uint32_t)kInvTabLen + (uint32_t)kInvPad;
+      uint32_t max_ip = 0, cmax = 0;
       // samples x0..x19; output words (prev,x0) (x1,x2) ... (x17,x18); x19 becomes prev.
       // A valid code is at most 10 bits, so three codes are parsed per 64-bit window.
 #pragma unroll
-      for (int i = 0; i < 20; i++) {
-        if (i % 3 == 0) { rd.window(hi, lo); cum = 0; }
-        if (i < 19 || !tail) {
-          X3_RICE_SAMPLE();
-          if ((i & 1) == 0) st[(i >> 1) * ss] = (prev & 0xffffu) | ((uint32_t)lw << 16);
-          else prev = (uint32_t)lw;
+      for (int g = 0; g < 7; g++) {
+        rd.window(hi, lo);
+        uint32_t cum = 0, ip0 = 0, ip1 = 0, ip2 = 0;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          const int i = 3 * g + j;
+          if (i < 20 && (i < 19 || !tail)) {
+            if (j == 0) X3_RICE_SAMPLE(ip0)
+            else if (j == 1) X3_RICE_SAMPLE(ip1)
+            else X3_RICE_SAMPLE(ip2)
+            if ((i & 1) == 0) st[(i >> 1) * ss] = pack_lo16(prev, (uint32_t)lw);
+            else prev = (uint32_t)lw;
+          }
         }
-        if (i % 3 == 2 || i == 19) {
-          cmax = cum > cmax ? cum : cmax;
-          rd.advance(cum > 32u ? 32u : cum);  // a longer group is malformed for this path; `bad` is set below
-        }
+        const uint32_t m12 = ip1 > ip2 ? ip1 : ip2, m0 = ip0 > max_ip ? ip0 : max_ip;
+        max_ip = m12 > m0 ? m12 : m0;
+        cmax = cum > cmax ? cum : cmax;
+        rd.advance(cum);  // a group longer than 32 bits is malformed for this path (`bad` below); the reader stays
+                          // inside its ring whatever it is given
       }
       // out-of-range index (decoder.rs:161,187; includes every zero run the 32-bit peek cannot see the end of)
       // or a group of codes longer than 32 bits (its later codes were parsed from the wrong place) -> the exact
       // path decides
-      if (max_ip >= inv_len + (uint32_t)level || cmax > 32u) bad = true;
+      if (max_ip >= ip_end || cmax > 32u) bad = true;
     } else {
       const uint32_t nb = ((hi >> 26) & 15u) + 1u;  // decoder.rs:211
       rd.advance(6);
@@ -292,7 +342,7 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
         for (int j = 0; j < 10; j++) {
           rd.window(hi, lo);
           lw = (int32_t)(hi >> 16);
-          st[j * ss] = (prev & 0xffffu) | ((uint32_t)lw << 16);
+          st[j * ss] = pack_lo16(prev, (uint32_t)lw);
           if (j < 9 || !tail) {
             lw = (int32_t)(hi & 0xffffu);
             prev = (uint32_t)lw;
@@ -309,7 +359,7 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
           int32_t v = (int32_t)(hi >> (32u - nb));
           if (v > half) v -= full;                    // unsigned_to_i16: strictly greater, decoder.rs:203
           lw += v;
-          st[j * ss] = (prev & 0xffffu) | ((uint32_t)lw << 16);
+          st[j * ss] = pack_lo16(prev, (uint32_t)lw);
           if (j < 9 || !tail) {
             v = (int32_t)(funnel_l(lo, hi, nb) >> (32u - nb));
             if (v > half) v -= full;

@@ -371,7 +371,10 @@ struct RingReader {
 __global__ void __launch_bounds__(kDecThreads, X3_DEC_MINBLOCKS) decode_frames_kernel(const DecodeArgs a) {
   __shared__ __align__(16) uint32_t s_ring[kDecThreads * kRingWords];
   __shared__ __align__(16) uint32_t s_stage[kDecThreads * kStageWords];  // [word][thread]
+  __shared__ int16_t s_inv[kInvTabEntries];
   const int tid = threadIdx.x;
+  for (int j = tid; j < kInvTabEntries; j += kDecThreads) s_inv[j] = inv_tab_entry(1 + j / kInvTabLen, j % kInvTabLen);
+  __syncthreads();
   const unsigned long long n = *a.n_frames < a.max_frames ? *a.n_frames : a.max_frames;
   const bool dflt = a.P.block_len == 20 && a.P.codes[0] == 0 && a.P.codes[1] == 1 && a.P.codes[2] == 3;
   const uint8_t *stream_end = a.stream + a.stream_len;
@@ -393,7 +396,7 @@ __global__ void __launch_bounds__(kDecThreads, X3_DEC_MINBLOCKS) decode_frames_k
         if (dflt && frame_fast_eligible(fr.samples, fr.payload_len, (uintptr_t)pl, (uintptr_t)out)) {
           RingReader rd;
           rd.start(pl, stream_end, s_ring + tid * kRingWords);
-          r = decode_frame_fast(rd, fr.payload_len, out, fr.samples, s_stage + tid, (uint32_t)kDecThreads);
+          r = decode_frame_fast(rd, fr.payload_len, out, fr.samples, s_stage + tid, (uint32_t)kDecThreads, s_inv);
           cp_async_wait_all();
         }
         if (r == kDecRetryExact) r = decode_frame_exact(pl, fr.payload_len, out, fr.samples, a.P);

@@ -335,3 +335,32 @@ def test_encode_host_pipelined_chunks(pkg, dev, oracle):
     out_len = C.c_size_t()
     rc = lib.x3_encode_host(pcm.ctypes.data, pcm.size, C.byref(ps), small.ctypes.data, small.size, C.byref(out_len), None)
     assert rc == pkg.error.BYTEWRITER_INSUFFICIENT_MEMORY
+
+
+def test_decode_host_pipelined_pieces(pkg, dev, oracle, monkeypatch):
+    """x3_decode_host cuts long streams into pieces at guessed frame starts and overlaps upload, decode and
+    download; the guess is proven per piece, and anything unclean falls back to the plain path.  Force the
+    pipeline on a small stream (several pieces) and compare with the oracle, clean and corrupted."""
+    p = pkg.x3.Parameters.default()
+    n = 123 * 10000 + 777
+    pcm = oracle.synth(4, 0x58330004, 384000, 0, n)
+    stream, _ = oracle.encode(pcm, threads=4)
+    monkeypatch.setenv("X3_DEC_PIPE_MIN_MB", "0")
+    monkeypatch.setenv("X3_DEC_PIPE_FIRST_KB", "16")
+    out, res = pkg.decoder.decode_stream(stream, p)
+    assert res.code == 0 and res.frames == 124 and res.frame_errors == 0 and np.array_equal(out, pcm)
+    rng = np.random.default_rng(5)
+    cases = []
+    for _ in range(6):      # a flipped payload bit somewhere: CRC error at that frame, earlier frames survive
+        s = stream.copy(); s[int(rng.integers(40, s.size))] ^= 1 << int(rng.integers(0, 8)); cases.append(s)
+    cases.append(stream[:stream.size - 1000].copy())                         # truncated last frame
+    cases.append(np.concatenate([stream, np.zeros(8, dtype=np.uint8)]))      # short tail
+    cases.append(np.concatenate([stream, np.zeros(64, dtype=np.uint8)]))     # long tail: header error
+    fake = stream.copy()                                                     # a header-like key inside a payload
+    fake[30000:30002] = (0x78, 0x33)
+    cases.append(fake)
+    for i, s in enumerate(cases):
+        rc, ref, frames_ok, ferr = oracle.decode_stream(s, n + 20000)
+        out, res = pkg.decoder.decode_stream(s, p, max_samples=n + 20000)
+        assert res.code == rc and res.frames == frames_ok and res.frame_errors == ferr, (i, res.code, rc)
+        assert out.size == ref.size and np.array_equal(out, ref), i

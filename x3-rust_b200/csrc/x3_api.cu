@@ -582,8 +582,12 @@ int host_walk(const uint8_t *s, size_t len, std::vector<FrameRec> &frames, unsig
 
 }  // namespace
 
-int x3_decode_device(const uint8_t *d_frames, size_t len, const x3_params *p, int16_t *d_pcm, size_t pcm_cap,
-                     size_t *n_out, x3_decode_result *res, void *cuda_stream) {
+namespace {
+// x3_decode_device; `consumed` (optional) receives the stream bytes covered by the frames found when the device
+// index was used and proven (0 otherwise)
+int decode_device_impl(const uint8_t *d_frames, size_t len, const x3_params *p, int16_t *d_pcm, size_t pcm_cap,
+                       size_t *n_out, x3_decode_result *res, void *cuda_stream, unsigned long long *consumed) {
+  if (consumed) *consumed = 0;
   Derived d;
   int rc = derive(p, &d);
   if (rc == X3_ERR_UNSUPPORTED_PARAMS) {
@@ -680,6 +684,7 @@ int x3_decode_device(const uint8_t *d_frames, size_t len, const x3_params *p, in
     if (host_res[2] != 0) need_walk = true;  // the table could not be proven equal to the reference's walk
     n_frames = host_res[4];
     total_samples = host_res[5];
+    if (consumed && !need_walk) *consumed = host_res[6];
     tl_ms[0] = t_dec.ms();
     tl_ms[1] = t_idx.ms();
     tl_ms[2] = t_all.ms();
@@ -750,6 +755,147 @@ int x3_decode_device(const uint8_t *d_frames, size_t len, const x3_params *p, in
   return ret;
 }
 
+// ---- pipelined host decode ----------------------------------------------------------------------
+// The stream is cut into a few pieces of geometrically growing size at frame starts GUESSED on the host (key 'x3'
+// + valid header at an even offset).  Pieces are uploaded back to back on one stream; each is indexed and decoded
+// as a stream of its own as soon as it has arrived, and its PCM goes back on a third stream while the next piece
+// is still uploading / decoding -- PCIe runs in both directions.  A guess is proven afterwards: piece j is the
+// reference's walk of its bytes (device chain check), it must decode without any error and must consume exactly
+// its byte range, i.e. end where piece j+1 starts.  Piece 0 starts at 0, so by induction every piece starts at a
+// true frame start.  If anything is off -- a bad frame, a piece that needed the host walk, a byte left over -- the
+// attempt is dropped and the whole stream is decoded by the plain path, which reports what the reference would.
+struct DecPipe {
+  int device = -1;
+  cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+thread_local DecPipe tl_dec;
+// tunables (read on every call so that tests can exercise the pipeline on small streams):
+// X3_DEC_PIPE_MIN_MB -- streams shorter than this take the plain path (default 48);
+// X3_DEC_PIPE_FIRST_KB -- size of the first piece (default 8192); each following piece is 4x larger, because the
+// PCM of a piece is ~4x its bytes, so its download hides the next piece's upload
+size_t env_size(const char *name, size_t dflt, unsigned shift) {
+  const char *s = getenv(name);
+  return s && *s ? (size_t)strtoull(s, nullptr, 10) << shift : dflt;
+}
+size_t decode_pipe_min() { return env_size("X3_DEC_PIPE_MIN_MB", (size_t)48 << 20, 20); }
+size_t decode_pipe_first() {
+  const size_t v = env_size("X3_DEC_PIPE_FIRST_KB", (size_t)8 << 20, 10);
+  return v < 4096 ? 4096 : v;
+}
+
+// first even offset >= from at which a plausible frame header starts (validated later), or len if none
+size_t guess_frame_start(const uint8_t *s, size_t len, size_t from) {
+  for (size_t pos = (from + 1) & ~(size_t)1; pos + 20 <= len; pos += 2) {
+    if (s[pos] != 'x' || s[pos + 1] != '3') continue;
+    x3_frame_header h;
+    if (x3_read_frame_header(s + pos, 20, &h) != X3_OK) continue;
+    const size_t next = pos + 20 + h.payload_len;
+    if (next + 20 <= len) {  // the following header must be valid too (cheap filter; the proof comes later)
+      x3_frame_header h2;
+      if (x3_read_frame_header(s + next, 20, &h2) != X3_OK) continue;
+    }
+    return pos;
+  }
+  return len;
+}
+
+// returns 1 if the pipelined attempt produced the final result (in *rc_out), 0 if the caller must use the plain path
+int decode_host_pipelined(const uint8_t *frames, size_t len, const x3_params *p, int16_t *pcm, size_t pcm_cap,
+                          size_t *n_out, x3_decode_result *res, int *rc_out) {
+  size_t cut[9];
+  int np = 0;
+  cut[0] = 0;
+  size_t want = decode_pipe_first();
+  while (np < 7) {
+    const size_t target = cut[np] + want;
+    if (target + (want >> 1) >= len) break;
+    const size_t c = guess_frame_start(frames, len, target);
+    if (c >= len || c <= cut[np]) break;
+    cut[++np] = c;
+    want *= 4;
+  }
+  cut[++np] = len;  // pieces [cut[j], cut[j+1]), j = 0..np-1
+  if (np < 2) return 0;
+
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  DecPipe &dp = tl_dec;
+  if (dp.device != dev || !dp.s_in) {
+    dp.device = dev;
+    if (cudaStreamCreateWithFlags(&dp.s_in, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&dp.s_cmp, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&dp.s_out, cudaStreamNonBlocking) != cudaSuccess) {
+      dp.s_in = nullptr;
+      return 0;
+    }
+    for (int i = 0; i < 8; i++)
+      if (cudaEventCreateWithFlags(&dp.ev[i], cudaEventDisableTiming) != cudaSuccess) { dp.s_in = nullptr; return 0; }
+  }
+  // device placement: every piece starts at a 256-byte aligned address (the index kernel loads 16 bytes at a time)
+  size_t doff[9], total = 0;
+  for (int j = 0; j < np; j++) { doff[j] = total; total += ((cut[j + 1] - cut[j]) + 16 + 255) & ~(size_t)255; }
+  uint8_t *d_in = nullptr;
+  int16_t *d_pcm = nullptr;
+  if (cudaMallocAsync(&d_in, total, dp.s_cmp) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (cudaMallocAsync(&d_pcm, (pcm_cap ? pcm_cap : 1) * sizeof(int16_t), dp.s_cmp) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFreeAsync(d_in, dp.s_cmp);
+    return 0;
+  }
+  cudaEvent_t ev_alloc = dp.ev[7];
+  cudaError_t e = cudaEventRecord(ev_alloc, dp.s_cmp);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(dp.s_in, ev_alloc, 0);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(dp.s_out, ev_alloc, 0);
+  for (int j = 0; j < np && e == cudaSuccess; j++) {
+    e = cudaMemcpyAsync(d_in + doff[j], frames + cut[j], cut[j + 1] - cut[j], cudaMemcpyHostToDevice, dp.s_in);
+    if (e == cudaSuccess) e = cudaEventRecord(dp.ev[j], dp.s_in);
+  }
+  bool clean = e == cudaSuccess;
+  unsigned long long samples = 0, nframes = 0;
+  float ms[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int j = 0; j < np && clean; j++) {
+    const size_t plen = cut[j + 1] - cut[j];
+    if (cudaStreamWaitEvent(dp.s_cmp, dp.ev[j], 0) != cudaSuccess) { clean = false; break; }
+    size_t got = 0;
+    x3_decode_result r;
+    unsigned long long consumed = 0;
+    const int rc = decode_device_impl(d_in + doff[j], plen, p, d_pcm + samples, pcm_cap - samples, &got, &r, dp.s_cmp, &consumed);
+    for (int k = 0; k < 4; k++) ms[k] += tl_ms[k];
+    // interior pieces must be consumed to the last byte; the last one may end in the <= 20 stray bytes or the
+    // truncated frame the reference tolerates -- but then it is the plain path that reports it
+    if (rc != X3_OK || r.first_bad_frame != UINT64_MAX || r.used_host_walk || consumed != plen) { clean = false; break; }
+    if (got && cudaMemcpyAsync(pcm + samples, d_pcm + samples, got * sizeof(int16_t), cudaMemcpyDeviceToHost, dp.s_out) != cudaSuccess) {
+      clean = false;
+      break;
+    }
+    samples += got;
+    nframes += r.frames;
+  }
+  e = cudaStreamSynchronize(dp.s_out);
+  const cudaError_t e2 = cudaStreamSynchronize(dp.s_in);
+  cudaFreeAsync(d_in, dp.s_cmp);
+  cudaFreeAsync(d_pcm, dp.s_cmp);
+  if (e != cudaSuccess || e2 != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (!clean) return 0;
+  if (res) {
+    memset(res, 0, sizeof *res);
+    res->first_bad_frame = UINT64_MAX;
+    res->frames = nframes;
+    res->samples = samples;
+  }
+  for (int k = 0; k < 4; k++) tl_ms[k] = ms[k];
+  *n_out = (size_t)samples;
+  *rc_out = X3_OK;
+  return 1;
+}
+}  // namespace
+
+int x3_decode_device(const uint8_t *d_frames, size_t len, const x3_params *p, int16_t *d_pcm, size_t pcm_cap,
+                     size_t *n_out, x3_decode_result *res, void *cuda_stream) {
+  return decode_device_impl(d_frames, len, p, d_pcm, pcm_cap, n_out, res, cuda_stream, nullptr);
+}
+
 int x3_decode_host(const uint8_t *frames, size_t len, const x3_params *p, int16_t *pcm, size_t pcm_cap, size_t *n_out,
                    x3_decode_result *res) {
   if (!n_out) return X3_ERR_INVALID_ARGUMENT;
@@ -763,6 +909,11 @@ int x3_decode_host(const uint8_t *frames, size_t len, const x3_params *p, int16_
   DeviceState *ds;
   int rc = device_state(&ds);
   if (rc) return rc;
+  if (len >= decode_pipe_min() && p) {
+    int prc = X3_OK;
+    if (decode_host_pipelined(frames, len, p, pcm, pcm_cap, n_out, res, &prc)) return prc;
+    *n_out = 0;
+  }
   uint8_t *d_in = nullptr;
   int16_t *d_pcm = nullptr;
   CU(cudaMallocAsync(&d_in, len + 16, st));

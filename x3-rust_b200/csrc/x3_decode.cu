@@ -209,9 +209,11 @@ __global__ void check_chain_kernel(const ScanArgs a) {
       if (end > a.stream_len) {
         a.result[4] = n - 1;  // truncated final frame: the reference stops cleanly before it
         a.result[5] = a.result[1] - fr.samples;
+        a.result[6] = fr.pos;  // bytes the walk consumed
       } else {
         a.result[4] = n;
         a.result[5] = a.result[1];
+        a.result[6] = end;
         if (a.stream_len - end > (unsigned long long)kFrameHeaderLen) atomicOr(a.result + 2, 1ull);
       }
     }

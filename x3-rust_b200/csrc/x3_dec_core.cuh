@@ -207,9 +207,13 @@ struct PlainBitReader {
   }
 };
 
-constexpr uint32_t kFastGroup = 80;        // samples per staged flush (4 blocks of 20 = 160 B = 5 whole sectors)
-constexpr uint32_t kStageWords = 40;       // staged words per thread; word j of thread t lives at stage[j*stride] with
-                                           // stride = threads per CTA on the device (conflict-free 32-bit accesses), 1 on the host
+constexpr uint32_t kFastGroup = 80;        // 4 blocks of 20 samples = 160 B = 5 whole 32-byte sectors of output
+constexpr uint32_t kStageWords = 16;       // staged words per thread; word j of thread t lives at stage[j*stride] with
+                                           // stride = threads per CTA on the device (conflict-free 32-bit accesses), 1 on the host.
+                                           // A block adds 10 words; whole sectors (8 words) leave after every block -- one
+                                           // after each of the first three blocks of a group, two after the fourth -- and the
+                                           // 2, 4 or 6 words left over move to the front.  (64 bytes instead of 160 per thread:
+                                           // shared memory is what limits the number of resident frames.)
 
 // Fast-path eligibility of a frame (Parameters::default() is checked by the caller).
 X3_HD bool frame_fast_eligible(uint32_t samples, uint32_t payload_len, uintptr_t payload_addr, uintptr_t out_addr) {
@@ -293,7 +297,8 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
   for (uint32_t b = 0; b < nblk; b++) {
     rd.block_begin();
     const bool tail = (b == nblk - 1u);
-    uint32_t *st = stage + (b & 3u) * 10u * ss;
+    const uint32_t t4 = b & 3u;               // position in the group of four blocks; 2*t4 words are waiting in the stage
+    uint32_t *st = stage + 2u * t4 * ss;
 
     rd.window(hi, lo);
     const uint32_t ftype = hi >> 30;
@@ -373,15 +378,25 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
       }
     }
     if (bad) break;
-    // ---- every fourth block: 160 staged bytes -> five whole 32-byte sectors of the output.  (Flushing 80 bytes
-    // every second block was measured: the half-written sectors cost ~10 % extra DRAM traffic and it was slower.)
-    if ((b & 3u) == 3u) {
-      uint4 *o = out4 + (size_t)(b >> 2) * 10u;
+    // ---- whole 32-byte sectors leave after every block (never a partial sector: half-written sectors were
+    // measured to cost ~10 % extra DRAM traffic) ----
+    {
+      uint4 *o = out4 + ((size_t)(b >> 2) * 5u + t4) * 2u;
+      uint4 v;
+      v.x = stage[0]; v.y = stage[ss]; v.z = stage[2u * ss]; v.w = stage[3u * ss];
+      o[0] = v;
+      v.x = stage[4u * ss]; v.y = stage[5u * ss]; v.z = stage[6u * ss]; v.w = stage[7u * ss];
+      o[1] = v;
+      if (t4 == 3u) {
+        v.x = stage[8u * ss]; v.y = stage[9u * ss]; v.z = stage[10u * ss]; v.w = stage[11u * ss];
+        o[2] = v;
+        v.x = stage[12u * ss]; v.y = stage[13u * ss]; v.z = stage[14u * ss]; v.w = stage[15u * ss];
+        o[3] = v;
+      } else {
+        const uint32_t left = 2u * t4 + 2u;
 #pragma unroll
-      for (int q = 0; q < 10; q++) {
-        uint4 v;
-        v.x = stage[(4 * q) * ss]; v.y = stage[(4 * q + 1) * ss]; v.z = stage[(4 * q + 2) * ss]; v.w = stage[(4 * q + 3) * ss];
-        o[q] = v;
+        for (uint32_t k = 0; k < 6u; k++)
+          if (k < left) stage[k * ss] = stage[(8u + k) * ss];
       }
     }
   }

@@ -277,7 +277,9 @@ int sim_decode_frame(const uint8_t *stream, size_t stream_len, size_t pos, uint3
     rd.init(pl, stream + stream_len);
     static int16_t inv[kInvTabEntries];
     for (int j = 0; j < kInvTabEntries; j++) inv[j] = inv_tab_entry(1 + j / kInvTabLen, j % kInvTabLen);
-    r = decode_frame_fast(rd, payload_len, out, samples, stage, 1u, inv);
+    RiceBlockPar par[4];
+    for (uint32_t f = 0; f < 4; f++) par[f] = rice_block_par(f);
+    r = decode_frame_fast(rd, payload_len, out, samples, stage, 1u, inv, par);
     if (r == kDecOk) *used_fast = 1;
   }
   if (r == kDecRetryExact) r = decode_frame_exact(pl, payload_len, out, samples, P);

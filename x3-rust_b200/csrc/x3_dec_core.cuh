@@ -221,18 +221,44 @@ X3_HD bool frame_fast_eligible(uint32_t samples, uint32_t payload_len, uintptr_t
          (payload_addr & 1u) == 0u && (out_addr & 31u) == 0u;
 }
 
-// Inverse-fold table of the fast path: for ftype f = 1..3 (level = 1, 2, 8) entry [ip + kInvPad] of table f is
-// INV_RICE_CODE[ip - level] (x3.rs:200-204), the delta of the code whose tracked index is ip = r + level*z.
-// ip reaches 31*8+15 when the zero run is as long as the 32-bit peek can see, and is -level..-level+15 (as a
-// signed number) when the peek is all zeros (z = 0xffffffff): both land inside the table, the frame is then flagged
-// through max_ip and decoded again by the exact path.  One shared-memory load replaces five ALU instructions.
-constexpr int kInvPad = 8;
-constexpr int kInvTabLen = kInvPad + 264;          // per ftype
+// Inverse-fold tables of the fast path.  A Rice code is z zeros, then nbk = k+1 bits r whose first bit is the
+// terminator; the reference's index is i = r + level*(z-1) with level = 2^k (decoder.rs:157-165, :184-191) and the
+// delta is INV_RICE_CODE[i] (x3.rs:200-204).  The kernel tracks q = z * 2^nbk + r instead -- the low word of the
+// funnel shift (z : t << z) >> (32 - nbk), ONE instruction once z is known -- and looks the delta up by q: entry
+// [q + kInvPad] of table f (f = ftype 1..3: nbk 1, 2, 4).  q is monotone in i over the codes that can occur
+// (r >= level, because t << z has its top bit set), so "some index out of range" is "max q >= inv_q_end(f)".
+// z is at most 31 when the 32-bit peek contains a one; an all-zero peek gives z = 0xffffffff on the device, for which
+// q is -2^nbk as a signed number (inside the pad, and huge as an unsigned one), and z = 32 on the host (q = 2^(nbk+5)).
+// Either way the frame goes to the exact path.
+constexpr int kInvPad = 16;
+constexpr int kInvTabLen = kInvPad + 512 + 8;      // per ftype
 constexpr int kInvTabEntries = 3 * kInvTabLen;
 X3_HD int16_t inv_tab_entry(int f /*1..3*/, int j /*0..kInvTabLen*/) {
-  const int level = f == 1 ? 1 : (f == 2 ? 2 : 8);
-  const int i = j - kInvPad - level;
+  const int nbk = f == 1 ? 1 : (f == 2 ? 2 : 4), level = 1 << (nbk - 1);
+  const int q = j - kInvPad;
+  if (q < 0) return 0;
+  const int z = q >> nbk, r = q & ((1 << nbk) - 1);
+  const int i = r + level * (z - 1);
   return i < 0 ? (int16_t)0 : (int16_t)unfold((uint32_t)i);
+}
+// first q (with r >= level) whose index i reaches inv_len = 16, 26, 60 (x3.rs:214,222,250):
+//   k=0: i = z        -> z = 16, r = 1;   k=1: i = r + 2(z-1) -> z = 13, r = 2;   k=3: i = r + 8(z-1) -> z = 7, r = 12
+X3_HD uint32_t inv_q_end(uint32_t f) { return f == 1u ? 33u : (f == 2u ? 54u : 124u); }
+
+// per-ftype constants of a Rice block, fetched with one 16-byte load
+struct alignas(16) RiceBlockPar {
+  uint32_t nbk;       // bits read after the zero run (decoder.rs:158,180)
+  uint32_t sh;        // 32 - nbk
+  uint32_t q_end;     // inv_q_end
+  uint32_t tab_off;   // entry of q = 0 in the table bank
+};
+X3_HD RiceBlockPar rice_block_par(uint32_t f) {
+  RiceBlockPar p;
+  p.nbk = f == 1u ? 1u : (f == 2u ? 2u : 4u);
+  p.sh = 32u - p.nbk;
+  p.q_end = inv_q_end(f);
+  p.tab_off = (f ? f - 1u : 0u) * (uint32_t)kInvTabLen + (uint32_t)kInvPad;
+  return p;
 }
 
 // hi32(a * b) + c and a * b + c as single FMA-pipe instructions (IMAD.HI.U32 / IMAD): the decoder is bound by the
@@ -263,26 +289,22 @@ X3_HD uint32_t pack_lo16(uint32_t lo, uint32_t hi) {  // (lo & 0xffff) | (hi << 
 #endif
 }
 
-// one Rice code at offset `cum` of the 64-bit window (decoder.rs:157-165 / :184-191 in closed form):
-//   z zeros, then nbk bits r of which the first is the terminator; index i = r + level*(z-1); delta = INV[i].
-// ip = i + level = r + level*z is what is tracked: r = (t << z) >> (32 - nbk) = hi32((t << z) * 2^nbk), so
-// ip = IMAD.HI(t << z, 2^nbk, IMAD(z, level, 0)); delta = tab[ip].
-// An all-zero window gives z = 0xffffffff on the device (32 on the host): t << z is 0, ip = -level (host: 32*level).
-#define X3_RICE_SAMPLE(ipv)                                                           \
+// one Rice code at offset `cum` of the 64-bit window: q = z * 2^nbk + r (see the table comment), delta = tab[q]
+#define X3_RICE_SAMPLE(qv)                                                            \
   {                                                                                   \
     const uint32_t t = funnel_l(lo, hi, cum);                                         \
     const uint32_t z = clz_shift(t);                                                  \
-    ipv = mad_hi_u32(shl_safe(t, z), pown, mad_lo_u32(z, level, 0u));                 \
-    cum += z + nbk;                                                                   \
-    lw += (int32_t)tab[(int32_t)ipv];                                                 \
+    qv = funnel_r(shl_safe(t, z), z, bp.sh);                                          \
+    cum += z + bp.nbk;                                                                \
+    lw += (int32_t)tab[(int32_t)qv];                                                  \
   }
 
 // Decode one frame.  `stage` = this thread's staging area: 40 words, `ss` words apart.
 // Returns kDecOk or kDecRetryExact.
-// `inv_tab` = kInvTabEntries entries built with inv_tab_entry (shared memory on the device).
+// `inv_tab` = kInvTabEntries entries built with inv_tab_entry, `par` = rice_block_par(0..3) (shared memory on the device).
 template <class Reader>
 X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint32_t samples, uint32_t *stage,
-                            const uint32_t ss, const int16_t *inv_tab) {
+                            const uint32_t ss, const int16_t *inv_tab, const RiceBlockPar *par) {
   uint32_t hi, lo;
   rd.block_begin();
   rd.window(hi, lo);
@@ -305,11 +327,8 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
     if (ftype != 0u) {
       // ---- Rice block: z zeros, then nbk bits of which the first is the terminator ----
       rd.advance(2);
-      const uint32_t nbk = ftype == 1u ? 1u : (ftype == 2u ? 2u : 4u);          // decoder.rs:158,180
-      const uint32_t level = ftype == 1u ? 1u : (ftype == 2u ? 2u : 8u);        // 1<<nsubs of RICE1 / RICE3
-      const uint32_t pown = 1u << nbk;
-      const uint32_t ip_end = ftype == 1u ? 17u : (ftype == 2u ? 28u : 68u);    // inv_len + level (x3.rs:214,222,250)
-      const int16_t *tab = inv_tab + (ftype - 1u) * (uint32_t)kInvTabLen + (uint32_t)kInvPad;
+      const RiceBlockPar bp = par[ftype];
+      const int16_t *tab = inv_tab + bp.tab_off;
       uint32_t max_ip = 0, cmax = 0;
       // samples x0..x19; output words (prev,x0) (x1,x2) ... (x17,x18); x19 becomes prev.
       // A valid code is at most 10 bits, so three codes are parsed per 64-bit window.
@@ -337,7 +356,7 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
       // out-of-range index (decoder.rs:161,187; includes every zero run the 32-bit peek cannot see the end of)
       // or a group of codes longer than 32 bits (its later codes were parsed from the wrong place) -> the exact
       // path decides
-      if (max_ip >= ip_end || cmax > 32u) bad = true;
+      if (max_ip >= bp.q_end || cmax > 32u) bad = true;
     } else {
       const uint32_t nb = ((hi >> 26) & 15u) + 1u;  // decoder.rs:211
       rd.advance(6);

@@ -374,8 +374,10 @@ __global__ void __launch_bounds__(kDecThreads, X3_DEC_MINBLOCKS) decode_frames_k
   __shared__ __align__(16) uint32_t s_ring[kDecThreads * kRingWords];
   __shared__ __align__(16) uint32_t s_stage[kDecThreads * kStageWords];  // [word][thread]
   __shared__ int16_t s_inv[kInvTabEntries];
+  __shared__ RiceBlockPar s_par[4];
   const int tid = threadIdx.x;
   for (int j = tid; j < kInvTabEntries; j += kDecThreads) s_inv[j] = inv_tab_entry(1 + j / kInvTabLen, j % kInvTabLen);
+  if (tid < 4) s_par[tid] = rice_block_par((uint32_t)tid);
   __syncthreads();
   const unsigned long long n = *a.n_frames < a.max_frames ? *a.n_frames : a.max_frames;
   const bool dflt = a.P.block_len == 20 && a.P.codes[0] == 0 && a.P.codes[1] == 1 && a.P.codes[2] == 3;
@@ -398,7 +400,7 @@ __global__ void __launch_bounds__(kDecThreads, X3_DEC_MINBLOCKS) decode_frames_k
         if (dflt && frame_fast_eligible(fr.samples, fr.payload_len, (uintptr_t)pl, (uintptr_t)out)) {
           RingReader rd;
           rd.start(pl, stream_end, s_ring + tid * kRingWords);
-          r = decode_frame_fast(rd, fr.payload_len, out, fr.samples, s_stage + tid, (uint32_t)kDecThreads, s_inv);
+          r = decode_frame_fast(rd, fr.payload_len, out, fr.samples, s_stage + tid, (uint32_t)kDecThreads, s_inv, s_par);
           cp_async_wait_all();
         }
         if (r == kDecRetryExact) r = decode_frame_exact(pl, fr.payload_len, out, fr.samples, a.P);

@@ -165,6 +165,28 @@ def reference_arm(args, rank, world):
     print(json.dumps(line))
 
 
+def bind_near_gpu(index):
+    """Pin this rank to the CPUs NVML reports as local to its GPU, so that the pinned host buffers of the e2e leg
+    (and the library's staging buffers) live on the GPU's NUMA node.  With several ranks per host the end-to-end
+    number is bound by host memory / PCIe root bandwidth, and remote-node buffers halve it.  Returns the number of
+    CPUs bound to, or 0 if the platform gives no answer (nothing changed then)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 64
+        masks = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(masks) for b in range(64) if (int(m) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return 0
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -188,6 +210,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs CUDA devices (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    numa_cpus = bind_near_gpu(local_rank)   # before any pinned allocation: first touch puts the pages on that node
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     pkg = importlib.import_module("x3-rust_b200")
@@ -300,7 +323,7 @@ def main():
         dt = float(tt.item())
         e2e = {"value": n_total / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(2 * n + elen),
                "d2h_bytes_per_step": int(elen + 2 * n), "ms_per_step": dt * 1e3, "steps": e2e_steps,
-               "api": "x3_encode_host + x3_decode_host (pinned host buffers)"}
+               "api": "x3_encode_host + x3_decode_host (pinned host buffers)", "cpus_bound_near_gpu": numa_cpus}
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
 

@@ -369,6 +369,14 @@ struct RingReader {
 #ifndef X3_DEC_ASMLD
 #define X3_DEC_ASMLD 0  // 1, 2: ld.shared from a precomputed 32-bit address (one instruction fewer, measured 2 % slower)
 #endif
+#if X3_DEC_ASMLD == 3
+    // load only in the lanes that cross a word boundary: fewer lanes per shared-memory access, fewer bank conflicts
+    // (the ring positions of the 32 lanes are unrelated, so every active lane is a potential conflict)
+    A = cross ? B : A;
+    B = cross ? C : B;
+    C = cross ? D : C;
+    if (cross) D = bswap32(ring[((pos >> 5) + 3u) & 31u]);
+#else
     uint32_t nd;
 #if X3_DEC_ASMLD == 1
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(nd) : "r"(rb + (((pos >> 3) + 12u) & 124u)) : "memory");
@@ -382,6 +390,7 @@ struct RingReader {
     B = cross ? C : B;
     C = cross ? D : C;
     D = cross ? nd : D;
+#endif
     s = s2 & 31u;
   }
   __device__ __forceinline__ uint32_t bits_used() const { return pos - pos0; }

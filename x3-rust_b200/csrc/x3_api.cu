@@ -109,6 +109,31 @@ struct Timer {
   }
 };
 
+// Payload CRC and frame decode are independent given the frame table: the CRC kernel runs on a second stream beside
+// the decode kernel and fills the SMs that kernel leaves idle while its last (serial) frames finish.
+struct DecodeFork {
+  int device = -1;
+  cudaStream_t s2 = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+thread_local DecodeFork tl_fork;
+cudaStream_t fork_stream() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  DecodeFork &f = tl_fork;
+  if (f.device != dev || !f.s2) {
+    f.device = dev;
+    if (cudaStreamCreateWithFlags(&f.s2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&f.join, cudaEventDisableTiming) != cudaSuccess) {
+      f.s2 = nullptr;
+      cudaGetLastError();
+      return nullptr;
+    }
+  }
+  return f.s2;
+}
+
 // ---- parameter handling -----------------------------------------------------------------------
 constexpr size_t kMaxDynSmem = 227 * 1024;
 
@@ -624,6 +649,7 @@ int decode_device_impl(const uint8_t *d_frames, size_t len, const x3_params *p, 
   const size_t o_res = take(64), o_dres = take(64), o_tick = take(64), o_tiles = take(8 * (size_t)n_tiles);
   const size_t zero_bytes = off;
   const size_t o_frames = take(sizeof(FrameRec) * max_frames), o_fstat = take(sizeof(int) * max_frames);
+  const size_t o_cstat = take(sizeof(int) * max_frames);
   unsigned char *ws = nullptr;
   CU(cudaMallocAsync(&ws, off, st));
   cudaError_t e = cudaMemsetAsync(ws, 0, zero_bytes, st);
@@ -652,10 +678,38 @@ int decode_device_impl(const uint8_t *d_frames, size_t len, const x3_params *p, 
   da.n_frames = sa.result + 4;
   da.max_frames = max_frames;
   da.frame_status = reinterpret_cast<int *>(ws + o_fstat);
+  da.crc_status = reinterpret_cast<int *>(ws + o_cstat);
   da.result = reinterpret_cast<unsigned long long *>(ws + o_dres);
   da.crc_tables = ds->crc_dev;
 
-  Timer t_all(st), t_idx(st), t_crc(st), t_dec(st);
+  cudaStream_t s2 = fork_stream();
+  if (!s2) s2 = st;  // no second stream: the two kernels simply run one after the other
+  Timer t_all(st), t_idx(st), t_crc(s2), t_dec(st);
+  // crc_frames on s2 beside decode_frames on st; st continues only when both are done
+  auto crc_and_decode = [&](unsigned long long hint) -> cudaError_t {
+    cudaError_t ee = cudaSuccess;
+    if (s2 != st) {
+      ee = cudaEventRecord(tl_fork.fork, st);
+      if (ee == cudaSuccess) ee = cudaStreamWaitEvent(s2, tl_fork.fork, 0);
+      if (ee != cudaSuccess) return ee;
+    }
+    // the decode kernel first: its CTAs take their places, the CRC kernel's CTAs get what is left and then every
+    // slot a finished decode CTA frees
+    t_dec.start();
+    ee = launch_decode(da, hint, st);
+    t_dec.stop();
+    if (ee != cudaSuccess) return ee;
+    t_crc.start();
+    ee = launch_crc(da, hint, s2);
+    t_crc.stop();
+    g_launches += 2;
+    if (ee != cudaSuccess) return ee;
+    if (s2 != st) {
+      ee = cudaEventRecord(tl_fork.join, s2);
+      if (ee == cudaSuccess) ee = cudaStreamWaitEvent(st, tl_fork.join, 0);
+    }
+    return ee;
+  };
   bool need_walk = (((uintptr_t)d_frames) & 15u) != 0;  // the scan uses 16-byte loads from the stream base
   int walk_rc = X3_OK;
   unsigned long long total_samples = 0, n_frames = 0;
@@ -667,15 +721,8 @@ int decode_device_impl(const uint8_t *d_frames, size_t len, const x3_params *p, 
     t_idx.stop();
     g_launches += 2;
     if (e != cudaSuccess) return fail(e, "scan_headers_kernel");
-    t_crc.start();
-    e = launch_crc(da, max_frames, st);
-    t_crc.stop();
-    if (e != cudaSuccess) return fail(e, "crc_frames_kernel");
-    t_dec.start();
-    e = launch_decode(da, max_frames, st);
-    t_dec.stop();
-    g_launches += 2;
-    if (e != cudaSuccess) return fail(e, "decode_frames_kernel");
+    e = crc_and_decode(max_frames);
+    if (e != cudaSuccess) return fail(e, "crc_frames_kernel / decode_frames_kernel");
     t_all.stop();
     e = cudaMemcpyAsync(host_res, ws + o_res, 64, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(host_res + 8, ws + o_dres, 8, cudaMemcpyDeviceToHost, st);
@@ -710,15 +757,7 @@ int decode_device_impl(const uint8_t *d_frames, size_t len, const x3_params *p, 
     if (e == cudaSuccess && n_frames)
       e = cudaMemcpyAsync(ws + o_frames, frames.data(), sizeof(FrameRec) * n_frames, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(ws + o_dres, 0xff, 8, st);
-    if (e == cudaSuccess && n_frames) {
-      t_crc.start();
-      e = launch_crc(da, n_frames, st);
-      t_crc.stop();
-      t_dec.start();
-      if (e == cudaSuccess) e = launch_decode(da, n_frames, st);
-      t_dec.stop();
-      g_launches += 2;
-    }
+    if (e == cudaSuccess && n_frames) e = crc_and_decode(n_frames);
     if (e == cudaSuccess) e = cudaMemcpyAsync(host_res + 8, ws + o_dres, 8, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return fail(e, "decode (host walk)");
@@ -730,13 +769,16 @@ int decode_device_impl(const uint8_t *d_frames, size_t len, const x3_params *p, 
   int ret = walk_rc;
   unsigned long long good_frames = n_frames, good_samples = total_samples;
   if (first_bad != ~0ull && first_bad < n_frames) {
-    int fstat = 0;
+    int fstat = 0, cstat = 0;
     FrameRec fr;
     e = cudaMemcpyAsync(&fstat, ws + o_fstat + sizeof(int) * first_bad, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(&cstat, ws + o_cstat + sizeof(int) * first_bad, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess)
       e = cudaMemcpyAsync(&fr, ws + o_frames + sizeof(FrameRec) * first_bad, sizeof(FrameRec), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return fail(e, "decode status read-back");
+    if (cstat != kDecOk) fstat = cstat;  // the reference checks the payload CRC before it decodes (decodefile.rs:93-103)
     good_frames = first_bad;
     good_samples = fr.out_off;
     res->first_bad_frame = first_bad;

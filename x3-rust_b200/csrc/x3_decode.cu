@@ -292,7 +292,10 @@ __global__ void __launch_bounds__(256) crc_frames_kernel(const DecodeArgs a) {
       }
       if ((s & 0xffffu) != fr.payload_crc) status = kDecErrPayloadCrc;  // decodefile.rs:97-100
     }
-    if (lane == 0) a.frame_status[f] = status;
+    if (lane == 0) {
+      a.crc_status[f] = status;
+      if (status != kDecOk) atomicMin(a.result, f);
+    }
   }
 }
 
@@ -413,8 +416,11 @@ __global__ void __launch_bounds__(kDecThreads, X3_DEC_MINBLOCKS) decode_frames_k
     const unsigned long long i = base + tid;
     if (i >= n) continue;
     const FrameRec fr = a.frames[i];
-    int status = a.frame_status[i];  // set by crc_frames_kernel
-    if (status == kDecOk) {
+    // The payload CRC is checked by crc_frames_kernel, which runs beside this kernel on another stream (it fills
+    // the SMs this kernel leaves idle while its last frames finish); the host combines the two verdicts.  Frames
+    // that kernel refuses to read (decodefile.rs:118-121 and truncation) are not decoded either.
+    int status = kDecOk;
+    if (fr.pos + kFrameHeaderLen + fr.payload_len <= a.stream_len && fr.payload_len <= kReadBufferSize) {
       if (fr.samples == 0u || fr.payload_len < 2u) {
         status = kDecErrPanic;
       } else if (fr.out_off + fr.samples > a.pcm_cap) {

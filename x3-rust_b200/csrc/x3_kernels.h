@@ -61,8 +61,10 @@ struct DecodeArgs {
   const FrameRec *frames;
   const unsigned long long *n_frames;  // device scalar (the index kernel produces it)
   unsigned long long max_frames;       // capacity of `frames` / status
-  int *frame_status;                   // [max_frames]
-  unsigned long long *result;          // [0] first bad frame (init ~0), [1] unused
+  int *frame_status;                   // [max_frames] verdict of decode_frames_kernel
+  int *crc_status;                     // [max_frames] verdict of crc_frames_kernel (runs concurrently with the decode;
+                                       // a frame's status is crc_status if that is an error, else frame_status)
+  unsigned long long *result;          // [0] first bad frame of either kernel (init ~0), [1] unused
   const uint16_t *crc_tables;
 };
 

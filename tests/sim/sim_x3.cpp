@@ -105,7 +105,6 @@ size_t sim_encode_frame_fast(const int16_t *pcm, uint32_t n, const CodecParams &
   std::vector<uint32_t> words((16u + nblk * 330u) / 32u + 16u, 0xdeadbeefu);
   struct Th { bool active, use_fast; uint32_t len, nbits, start, bit_off; FastBlock fb; BlockMode mode; };
   std::vector<Th> th(512);
-  std::vector<uint32_t> s_first(512, 0xdeadbeefu);
   uint32_t run = 0;
   for (int tid = 0; tid < 512; tid++) {
     Th &t = th[tid];
@@ -128,17 +127,22 @@ size_t sim_encode_frame_fast(const int16_t *pcm, uint32_t n, const CodecParams &
   const uint32_t total_bits = run, payload_len = payload_bytes(total_bits);
   std::vector<int16_t> s_in_pack = s_in;
   if (!last_frame) std::fill(s_in_pack.begin(), s_in_pack.end(), (int16_t)0x7b7b);  // next frame's prefetch
+  std::vector<uint32_t> tail(512, 0u);
+  std::vector<uint32_t *> tail_at(512, nullptr);
   for (int tid = 0; tid < 512; tid++) {
     Th &t = th[tid];
     if (!t.active) continue;
     FastSink sink;
-    sink.init(t.bit_off, words.data(), &s_first[tid]);
+    sink.init(t.bit_off, words.data());
     if (tid == 0) { sink.put((uint32_t)(uint16_t)(t.use_fast ? t.fb.pred : (int32_t)s_in_pack[0]), 16); sink.flush(); }
     if (t.use_fast) block_pack_fast(t.fb, t.len, t.mode, sink);
-    else { if (t.len > 0) block_pack_generic(s_in_pack.data(), t.start, t.len, t.mode, sink); sink.finish(); }
+    else if (t.len > 0) block_pack_generic(s_in_pack.data(), t.start, t.len, t.mode, sink);
+    tail[tid] = sink.finish_tail();
+    if (sink.cnt) tail_at[tid] = sink.dst;
   }
+  if (total_bits & 31u) words[total_bits >> 5] = 0u;   // tid 0, before the barrier
   for (int tid = 0; tid < 512; tid++)
-    if (th[tid].active && (th[tid].bit_off & 31u)) words[th[tid].bit_off >> 5] |= s_first[tid];  // atomicOr
+    if (tail_at[tid]) *tail_at[tid] |= tail[tid];        // shared-memory OR after the barrier
   const uint32_t crc = crc_sliced(words.data(), payload_len);
   const uint32_t hc = header_crc(T(), 1u, n, payload_len);
   uint32_t hdr[5] = {bswap32((kFrameKey << 16) | 0x0101u), bswap32(((n & 0xffffu) << 16) | (payload_len & 0xffffu)), 0u, 0u,

@@ -275,80 +275,79 @@ X3_HD BlockMode block_measure_fast(const int16_t *s, uint32_t start, uint32_t le
   return m;
 }
 
-// shared-memory word address: a 32-bit shared-window address on the device (so address selects are one
+// shared-memory word address: a 32-bit shared-window address on the device (so address arithmetic is one
 // instruction), a plain pointer in the CPU simulation
 #if defined(__CUDA_ARCH__)
 typedef uint32_t smaddr_t;
 X3_HD smaddr_t sm_addr(const uint32_t *p) { return (smaddr_t)__cvta_generic_to_shared(p); }
-X3_HD void sm_store(smaddr_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 X3_HD void sm_store_if(bool pred, smaddr_t a, uint32_t v) {
   asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.shared.u32 [%0], %1; }" ::"r"(a), "r"(v), "r"((uint32_t)pred) : "memory");
 }
-X3_HD smaddr_t sm_next(smaddr_t a) { return a + 4u; }
+X3_HD smaddr_t sm_advance(smaddr_t a, uint32_t words) { return a + 4u * words; }
+X3_HD void sm_or(smaddr_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 #else
 typedef uint32_t *smaddr_t;
 X3_HD smaddr_t sm_addr(uint32_t *p) { return p; }
-X3_HD void sm_store(smaddr_t a, uint32_t v) { *a = v; }
 X3_HD void sm_store_if(bool pred, smaddr_t a, uint32_t v) { if (pred) *a = v; }
-X3_HD smaddr_t sm_next(smaddr_t a) { return a + 1; }
+X3_HD smaddr_t sm_advance(smaddr_t a, uint32_t words) { return a + words; }
+X3_HD void sm_or(smaddr_t a, uint32_t v) { *a |= v; }
 #endif
 
-// MSB-first bit sink of the fast kernel.  A block whose first bit is not word aligned keeps its first word
-// out of the image (it goes to `first_slot`) and ORs it into place with one shared-memory atomic after all
-// plain stores are done; every other word -- including the zero-padded last partial word -- is a plain store
-// to its final position.  (The predecessor's last word, stored plainly, is the base the head is ORed into.)
-// flush() is branch free: a predicated store and three selects.
+// MSB-first bit sink of the fast kernel.  Words are written while packing to their final position in the image by
+// the block that holds their LAST bit (a plain store of the whole word; the bits before the block's first bit are
+// zero in it).  A block's last, partial word is not stored: finish_tail() returns it (zero padded) and the caller
+// ORs it into place with one shared-memory reduction after every plain store is done -- by then the word has been
+// stored by the block that completes it, or zeroed by the caller if it is the frame's last.  No second pointer and
+// no select: flush() is a compare, a funnel shift, a byte swap, a predicated store and two updates.
 struct FastSink {
   uint64_t acc;
   uint32_t cnt;
   smaddr_t dst;
-  smaddr_t nxt;
-  X3_HD void init(uint32_t bit_off, uint32_t *out_words, uint32_t *first_slot) {
+  X3_HD void init(uint32_t bit_off, uint32_t *out_words) {
     acc = 0;
     cnt = bit_off & 31u;
-    uint32_t *w = out_words + (bit_off >> 5);
-    dst = cnt ? sm_addr(first_slot) : sm_addr(w);
-    nxt = sm_addr(w + 1);
+    dst = sm_addr(out_words + (bit_off >> 5));
   }
   X3_HD void put(uint32_t v, uint32_t n) {  // v < 2^n, n <= 32, cnt + n <= 64
     acc = (acc << n) | (uint64_t)v;
     cnt += n;
   }
   X3_HD void flush() {
-    const bool f = cnt >= 32u;
-    const uint32_t nc = cnt - 32u;
-    sm_store_if(f, dst, bswap32((uint32_t)(acc >> (nc & 31u))));
-    dst = f ? nxt : dst;
-    nxt = f ? sm_next(nxt) : nxt;
-    cnt = f ? nc : cnt;
+    const uint32_t full = cnt >> 5;         // 0 or 1
+    sm_store_if(full != 0u, dst, bswap32((uint32_t)(acc >> (cnt & 31u))));   // cnt in [32,63]: acc >> (cnt - 32)
+    dst = sm_advance(dst, full);
+    cnt &= 31u;
   }
-  X3_HD void finish() {
+  X3_HD uint32_t finish_tail() {            // the word at dst, valid if cnt != 0 afterwards
     flush();
-    if (cnt) sm_store(dst, bswap32((uint32_t)(acc << (32u - cnt))));
+    return cnt ? bswap32((uint32_t)(acc << (32u - cnt))) : 0u;
   }
 };
 
-// Fast-path packer.  Rice codewords are at most 10 bits at the default thresholds, so three of them are first
-// merged in a 32-bit register and appended with one 64-bit shift; BFP / literal samples go in pairs.
+// Fast-path packer (no finish: the caller takes the tail).  Rice codewords are at most 10 bits at the default
+// thresholds, so three of them are first merged in a 32-bit register -- Horner with the powers of two 2^len as
+// multipliers, i.e. two IMADs on the FMA pipe instead of shifts and ORs on the ALU pipe -- and appended with one
+// 64-bit shift; BFP / literal samples go in pairs.
 X3_HD void block_pack_fast(const FastBlock &fb, uint32_t len, const BlockMode &m, FastSink &sink) {
   const bool full = len == (uint32_t)kFastBL;
   if (m.kind == kRice) {
     sink.put(m.hdr, 2);
-    const uint32_t k = m.k, marker = 1u << k, mask = marker - 1u, k1 = k + 1u;
+    const uint32_t k = m.k, marker = 1u << k, mask = marker - 1u, k1 = k + 1u, K1 = 2u << k, n3 = 3u * k1;
 #pragma unroll
     for (int t = 0; t < 6; t++) {
       const uint32_t u0 = fb.u[3 * t], u1 = fb.u[3 * t + 1], u2 = fb.u[3 * t + 2];
-      const uint32_t l2 = (u2 >> k) + k1;
-      const uint32_t l12 = (u1 >> k) + k1 + l2;
-      const uint32_t v = ((marker | (u0 & mask)) << l12) | ((marker | (u1 & mask)) << l2) | (marker | (u2 & mask));
-      sink.put(v, (u0 >> k) + k1 + l12);
+      const uint32_t q0 = u0 >> k, q1 = u1 >> k, q2 = u2 >> k;
+      const uint32_t b0 = marker | (u0 & mask), b1 = marker | (u1 & mask), b2 = marker | (u2 & mask);
+      const uint32_t v = (b0 * (K1 << q1) + b1) * (K1 << q2) + b2;   // b0 : b1 : b2 with lengths q+k1
+      sink.put(v, q0 + q1 + q2 + n3);
       sink.flush();
     }
     {
       const uint32_t u0 = fb.u[18], u1 = fb.u[19];
-      const uint32_t l1 = full ? (u1 >> k) + k1 : 0u;
-      const uint32_t c1 = full ? (marker | (u1 & mask)) : 0u;
-      sink.put(((marker | (u0 & mask)) << l1) | c1, (u0 >> k) + k1 + l1);
+      const uint32_t q0 = u0 >> k, q1 = u1 >> k;
+      const uint32_t b0 = marker | (u0 & mask), b1 = marker | (u1 & mask);
+      const uint32_t p1 = full ? (K1 << q1) : 1u, c1 = full ? b1 : 0u, l1 = full ? q1 + k1 : 0u;
+      sink.put(b0 * p1 + c1, q0 + k1 + l1);
     }
   } else if (m.kind == kBfp) {
     sink.put(m.hdr, 6);
@@ -375,7 +374,6 @@ X3_HD void block_pack_fast(const FastBlock &fb, uint32_t len, const BlockMode &m
       sink.flush();
     }
   }
-  sink.finish();
 }
 
 // payload bytes for a payload of total_bits bits: pad to a byte, then to an even length

@@ -475,7 +475,6 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const __grid
   const uint32_t img_words = img_bytes >> 2;
   uint16_t *s_crcT = reinterpret_cast<uint16_t *>(p);             p += kCrcBankEntries2 * 2;
   const uint16_t *s_crcT2 = s_crcT + kCrcTableEntries;            // byte-swapped bank (worker CRC)
-  uint32_t *s_first = reinterpret_cast<uint32_t *>(p);            p += 512 * 4;
   uint32_t *s_V = reinterpret_cast<uint32_t *>(p);                p += NB * kMaxSlices * 4;
   uint32_t *s_misc = reinterpret_cast<uint32_t *>(p);
   const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(s_misc + 80);  // 8 bytes: the frame stager's mbarrier
@@ -667,27 +666,30 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const __grid
     // ---- prefetch the next frame, pack this one ----
     const uint32_t warp_base = __shfl_sync(0xffffffffu, wincl - wt, wid);
     const uint32_t bit_off = warp_base + (incl - nbits);
+    FastSink sink;
+    uint32_t tail = 0;
+    sink.cnt = 0;
     if (active) {
-      FastSink sink;
-      sink.init(bit_off, s_words, &s_first[tid]);
+      sink.init(bit_off, s_words);
       if (b == 0) {
         sink.put((uint32_t)(uint16_t)(use_fast ? fb.pred : (int32_t)s_in[0]), 16);
         sink.flush();
       }
-      if (use_fast) {
-        block_pack_fast(fb, len, mode, sink);
-      } else {
-        if (len > 0) block_pack_generic(s_in, start, len, mode, sink);
-        sink.finish();
-      }
+      if (use_fast) block_pack_fast(fb, len, mode, sink);
+      else if (len > 0) block_pack_generic(s_in, start, len, mode, sink);
+      tail = sink.finish_tail();   // this block's last, partial word: ORed in after barrier (D)
     }
-    if (tid == 0) s_misc[32] = atomicAdd(a.ticket, 1u);  // this CTA's next frame
+    if (tid == 0) {
+      s_misc[32] = atomicAdd(a.ticket, 1u);  // this CTA's next frame
+      // the frame's last word is completed by nobody: zero it for the tails that are ORed into it (and for the padding)
+      if (total_bits & 31u) s_words[total_bits >> 5] = 0u;
+    }
     X3_T(4)
     bar_workers();  // (D) every plain store done
     X3_T(5)
     uint32_t f_next = s_misc[32];
     if (f_next >= a.n_frames) f_next = kNoFrame;
-    if (active && (bit_off & 31u)) atomicOr(&s_words[bit_off >> 5], s_first[tid]);
+    if (sink.cnt) sm_or(sink.dst, tail);
     X3_T(6)
     bar_workers();  // (E) payload image complete
     X3_T(7)
@@ -802,7 +804,7 @@ size_t encode_smem_bytes(const CodecParams &P, uint32_t max_blocks, uint32_t out
 size_t encode_fast_smem_bytes(const CodecParams &P, uint32_t out_words_cap) {
   const uint32_t in_bytes = (2u * (P.spf + 8u) + 15u) & ~15u;
   const uint32_t img_bytes = (4u * (out_words_cap + 8u) + 15u) & ~15u;
-  return (size_t)in_bytes + NB * img_bytes + kCrcBankEntries2 * 2 + 512u * 4u + NB * kMaxSlices * 4u + 96u * 4u;
+  return (size_t)in_bytes + NB * img_bytes + kCrcBankEntries2 * 2 + NB * kMaxSlices * 4u + 96u * 4u;
 }
 
 cudaError_t launch_encode(const EncodeArgs &a, bool fast, int grid, size_t smem, cudaStream_t stream) {

@@ -89,22 +89,42 @@ int pinned(unsigned long long **out) {
   return X3_OK;
 }
 
+// CUDA event pairs for the kernel timings behind x3_last_kernel_ms.  Creating and destroying eight events per call
+// cost more host time than the calls' own launches, so each thread keeps a small pool.
+struct EventPool {
+  cudaEvent_t ev[16];
+  int n = 0, used = 0, device = -1;
+};
+thread_local EventPool tl_events;
+cudaEvent_t pooled_event() {
+  EventPool &p = tl_events;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (p.device != dev) { p.device = dev; p.n = 0; p.used = 0; }  // events of another device are left to teardown
+  if (p.used < p.n) return p.ev[p.used++];
+  cudaEvent_t e = nullptr;
+  if (p.n < 16 && cudaEventCreate(&e) == cudaSuccess) {
+    p.ev[p.n++] = e;
+    p.used = p.n;
+    return e;
+  }
+  cudaGetLastError();
+  return nullptr;
+}
+void release_pooled_events() { tl_events.used = 0; }   // at the start of every call that times kernels
+
 struct Timer {
   cudaEvent_t a = nullptr, b = nullptr;
   cudaStream_t s;
   explicit Timer(cudaStream_t st) : s(st) {
-    cudaEventCreate(&a);
-    cudaEventCreate(&b);
+    a = pooled_event();
+    b = pooled_event();
   }
-  ~Timer() {
-    if (a) cudaEventDestroy(a);
-    if (b) cudaEventDestroy(b);
-  }
-  void start() { cudaEventRecord(a, s); }
-  void stop() { cudaEventRecord(b, s); }
+  void start() { if (a) cudaEventRecord(a, s); }
+  void stop() { if (b) cudaEventRecord(b, s); }
   float ms() {
     float t = 0.f;
-    if (cudaEventElapsedTime(&t, a, b) != cudaSuccess) { cudaGetLastError(); return 0.f; }
+    if (!a || !b || cudaEventElapsedTime(&t, a, b) != cudaSuccess) { cudaGetLastError(); return 0.f; }
     return t;
   }
 };
@@ -396,6 +416,7 @@ int x3_encode_device(const int16_t *d_pcm, size_t n_samples, const x3_params *p,
   const size_t ws_bytes = encode_ws_bytes(nf);
   unsigned char *ws = nullptr;
   CU(cudaMallocAsync(&ws, ws_bytes, st));
+  release_pooled_events();
   Timer tm(st);
   tm.start();
   cudaError_t e = enqueue_encode(d, ds, d_pcm, n_samples, d_out, out_cap, ws, st, &rc);
@@ -684,6 +705,7 @@ int decode_device_impl(const uint8_t *d_frames, size_t len, const x3_params *p, 
 
   cudaStream_t s2 = fork_stream();
   if (!s2) s2 = st;  // no second stream: the two kernels simply run one after the other
+  release_pooled_events();
   Timer t_all(st), t_idx(st), t_crc(s2), t_dec(st);
   // crc_frames on s2 beside decode_frames on st; st continues only when both are done
   auto crc_and_decode = [&](unsigned long long hint) -> cudaError_t {

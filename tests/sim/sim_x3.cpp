@@ -279,7 +279,7 @@ int sim_decode_frame(const uint8_t *stream, size_t stream_len, size_t pos, uint3
     alignas(16) uint32_t stage[kStageWords];
     PlainBitReader rd;
     rd.init(pl, stream + stream_len);
-    static int16_t inv[kInvTabEntries];
+    static inv_entry_t inv[kInvTabEntries];
     for (int j = 0; j < kInvTabEntries; j++) inv[j] = inv_tab_entry(1 + j / kInvTabLen, j % kInvTabLen);
     RiceBlockPar par[4];
     for (uint32_t f = 0; f < 4; f++) par[f] = rice_block_par(f);

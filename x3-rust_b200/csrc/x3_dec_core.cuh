@@ -233,13 +233,18 @@ X3_HD bool frame_fast_eligible(uint32_t samples, uint32_t payload_len, uintptr_t
 constexpr int kInvPad = 16;
 constexpr int kInvTabLen = kInvPad + 512 + 8;      // per ftype
 constexpr int kInvTabEntries = 3 * kInvTabLen;
-X3_HD int16_t inv_tab_entry(int f /*1..3*/, int j /*0..kInvTabLen*/) {
+// Entries are ONE BYTE (every delta of a valid index fits: |INV_RICE_CODE[i]| <= 30 for i < 60): with four entries per
+// 32-bit word the valid q of a table span at most 32 words (k=3: q <= 123), so two lanes that look up different
+// codes never hit different words of the same bank -- the lookups are free of bank conflicts.  (With 16-bit entries
+// the zero runs z and z+4 of a k=3 block collided.)
+typedef int8_t inv_entry_t;
+X3_HD inv_entry_t inv_tab_entry(int f /*1..3*/, int j /*0..kInvTabLen*/) {
   const int nbk = f == 1 ? 1 : (f == 2 ? 2 : 4), level = 1 << (nbk - 1);
   const int q = j - kInvPad;
   if (q < 0) return 0;
   const int z = q >> nbk, r = q & ((1 << nbk) - 1);
   const int i = r + level * (z - 1);
-  return i < 0 ? (int16_t)0 : (int16_t)unfold((uint32_t)i);
+  return (i < 0 || i >= 64) ? (inv_entry_t)0 : (inv_entry_t)unfold((uint32_t)i);   // i >= inv_len is flagged via q_end
 }
 // first q (with r >= level) whose index i reaches inv_len = 16, 26, 60 (x3.rs:214,222,250):
 //   k=0: i = z        -> z = 16, r = 1;   k=1: i = r + 2(z-1) -> z = 13, r = 2;   k=3: i = r + 8(z-1) -> z = 7, r = 12
@@ -325,7 +330,7 @@ X3_HD uint32_t pack_lo16(uint32_t lo, uint32_t hi) {  // (lo & 0xffff) | (hi << 
 // `inv_tab` = kInvTabEntries entries built with inv_tab_entry, `par` = rice_block_par(0..3) (shared memory on the device).
 template <class Reader>
 X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint32_t samples, uint32_t *stage,
-                            const uint32_t ss, const int16_t *inv_tab, const RiceBlockPar *par) {
+                            const uint32_t ss, const inv_entry_t *inv_tab, const RiceBlockPar *par) {
   uint32_t hi, lo;
   rd.block_begin();
   rd.window(hi, lo);
@@ -349,7 +354,7 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
       // ---- Rice block: z zeros, then nbk bits of which the first is the terminator ----
       rd.advance(2);
       const RiceBlockPar bp = par[ftype];
-      const int16_t *tab = inv_tab + bp.tab_off;
+      const inv_entry_t *tab = inv_tab + bp.tab_off;
       uint32_t max_ip = 0, cmax = 0;
       // samples x0..x19; output words (prev,x0) (x1,x2) ... (x17,x18); x19 becomes prev.
       // A valid code is at most 10 bits, so X3_DEC_GROUP = 3 codes fit the 32 bits one reader step may consume.

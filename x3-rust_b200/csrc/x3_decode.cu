@@ -402,7 +402,7 @@ struct RingReader {
 __global__ void __launch_bounds__(kDecThreads, X3_DEC_MINBLOCKS) decode_frames_kernel(const DecodeArgs a) {
   __shared__ __align__(16) uint32_t s_ring[kDecThreads * kRingWords];
   __shared__ __align__(16) uint32_t s_stage[kDecThreads * kStageWords];  // [word][thread]
-  __shared__ int16_t s_inv[kInvTabEntries];
+  __shared__ __align__(16) inv_entry_t s_inv[kInvTabEntries];
   __shared__ RiceBlockPar s_par[4];
   const int tid = threadIdx.x;
   for (int j = tid; j < kInvTabEntries; j += kDecThreads) s_inv[j] = inv_tab_entry(1 + j / kInvTabLen, j % kInvTabLen);

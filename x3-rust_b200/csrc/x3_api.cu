@@ -667,10 +667,12 @@ int decode_device_impl(const uint8_t *d_frames, size_t len, const x3_params *p, 
   // workspace layout
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-  const size_t o_res = take(64), o_dres = take(64), o_tick = take(64), o_tiles = take(8 * (size_t)n_tiles);
+  const size_t o_res = take(64), o_dres = take(64), o_tick = take(64);
   const size_t zero_bytes = off;
+  const size_t o_tiles = take(8 * (size_t)n_tiles), o_trecs = take(8 * (size_t)n_tiles);
   const size_t o_frames = take(sizeof(FrameRec) * max_frames), o_fstat = take(sizeof(int) * max_frames);
   const size_t o_cstat = take(sizeof(int) * max_frames);
+  const size_t o_recs = take(sizeof(FrameRec) * max_frames);
   unsigned char *ws = nullptr;
   CU(cudaMallocAsync(&ws, off, st));
   cudaError_t e = cudaMemsetAsync(ws, 0, zero_bytes, st);
@@ -683,8 +685,11 @@ int decode_device_impl(const uint8_t *d_frames, size_t len, const x3_params *p, 
   sa.stream_len = len;
   sa.frames = reinterpret_cast<FrameRec *>(ws + o_frames);
   sa.max_frames = max_frames;
+  sa.recs = reinterpret_cast<FrameRec *>(ws + o_recs);
   sa.tile_status = reinterpret_cast<unsigned long long *>(ws + o_tiles);
   sa.ticket = reinterpret_cast<unsigned int *>(ws + o_tick);
+  sa.rec_cursor = reinterpret_cast<unsigned long long *>(ws + o_tick + 8);
+  sa.tile_recs = reinterpret_cast<unsigned long long *>(ws + o_trecs);
   sa.result = reinterpret_cast<unsigned long long *>(ws + o_res);
   sa.crc_tables = ds->crc_dev;
   sa.n_tiles = n_tiles;
@@ -741,7 +746,7 @@ int decode_device_impl(const uint8_t *d_frames, size_t len, const x3_params *p, 
     e = launch_scan(sa, st);
     if (e == cudaSuccess) e = launch_chain_check(sa, st);
     t_idx.stop();
-    g_launches += 2;
+    g_launches += 4;
     if (e != cudaSuccess) return fail(e, "scan_headers_kernel");
     e = crc_and_decode(max_frames);
     if (e != cudaSuccess) return fail(e, "crc_frames_kernel / decode_frames_kernel");

@@ -140,43 +140,96 @@ __global__ void __launch_bounds__(kScanThreads) scan_headers_kernel(const ScanAr
     }
     __syncthreads();
 
-    // ---- frame ordinal and sample offset of the tile's first frame: look-back over tiles ----
+    // ---- hand the tile's frames over, in order, with sample offsets relative to the tile; the tile's place in the
+    // stream (frame ordinal and sample offset of its first frame) is worked out afterwards by tile_prefix_kernel and
+    // place_frames_kernel.  (A decoupled look-back here made every CTA wait, once per tile, for all the tiles in
+    // flight before it: 40 % of the kernel's time.) ----
     if (tid < 32) {
       for (uint32_t j = tid; j < cnt; j += 32) tile_samples += s_cand[j].samples;
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) tile_samples += __shfl_xor_sync(0xffffffffu, tile_samples, d);
-      const unsigned long long own = ((unsigned long long)cnt << kCountShift) | tile_samples;
-      if (tid == 0) st_status(a.tile_status + tile, (tile == 0 ? kFlagPrefix : kFlagAgg) | own);
-      const unsigned long long excl = lookback_exclusive(a.tile_status, tile, own);
       if (tid == 0) {
-        s_base = excl;
-        if (tile == a.n_tiles - 1) {
-          const unsigned long long tot = excl + own;
-          a.result[0] = tot >> kCountShift;
-          a.result[1] = tot & ((1ull << kCountShift) - 1ull);
-        }
+        const unsigned long long off = atomicAdd(a.rec_cursor, (unsigned long long)cnt);
+        s_base = off;
+        a.tile_status[tile] = ((unsigned long long)cnt << kCountShift) | tile_samples;
+        a.tile_recs[tile] = (off << 11) | cnt;   // cnt <= kScanCap = 1024
       }
     }
     __syncthreads();
-    const unsigned long long base_count = s_base >> kCountShift;
-    const unsigned long long base_samples = s_base & ((1ull << kCountShift) - 1ull);
+    const unsigned long long rec_off = s_base;
     for (uint32_t r = tid; r < cnt; r += kScanThreads) {
       const Cand c = s_cand[s_rank[r]];
       unsigned long long before = 0;
       for (uint32_t m = 0; m < r; m++) before += s_cand[s_rank[m]].samples;
-      const unsigned long long ord = base_count + r;
-      if (ord < a.max_frames) {
+      if (rec_off + r < a.max_frames) {
         FrameRec fr;
         fr.pos = t0 + c.off;
-        fr.out_off = base_samples + before;
+        fr.out_off = before;
         fr.samples = c.samples;
         fr.payload_len = c.payload_len;
         fr.payload_crc = c.payload_crc;
         fr.pad = 0;
-        a.frames[ord] = fr;
+        a.recs[rec_off + r] = fr;
       } else {
         atomicOr(a.result + 2, 1ull);
       }
+    }
+  }
+}
+
+// Exclusive prefix over the tiles of (frames << 38 | samples), in place; totals to result[0], result[1].  One CTA.
+__global__ void __launch_bounds__(1024) tile_prefix_kernel(const ScanArgs a) {
+  __shared__ unsigned long long s_warp[32];
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+  const uint32_t per = (a.n_tiles + 1023u) / 1024u;
+  const uint32_t t0 = tid * per, t1 = t0 + per < a.n_tiles ? t0 + per : a.n_tiles;
+  unsigned long long sum = 0;
+  for (uint32_t t = t0; t < t1; t++) sum += a.tile_status[t];
+  unsigned long long incl = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= (uint32_t)d) incl += o;
+  }
+  if (lane == 31u) s_warp[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    unsigned long long w = s_warp[lane], wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long o = __shfl_up_sync(0xffffffffu, wi, d);
+      if (lane >= (uint32_t)d) wi += o;
+    }
+    s_warp[lane] = wi - w;  // exclusive over warps
+    if (lane == 31u) {
+      a.result[0] = wi >> kCountShift;
+      a.result[1] = wi & ((1ull << kCountShift) - 1ull);
+    }
+  }
+  __syncthreads();
+  unsigned long long run = s_warp[wid] + incl - sum;
+  for (uint32_t t = t0; t < t1; t++) {
+    const unsigned long long own = a.tile_status[t];
+    a.tile_status[t] = run;
+    run += own;
+  }
+}
+
+// One warp per tile: the tile's records go to their final place in the frame table.
+__global__ void __launch_bounds__(256) place_frames_kernel(const ScanArgs a) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < a.n_tiles; t += warps) {
+    const unsigned long long tr = a.tile_recs[t], base = a.tile_status[t];
+    const uint32_t cnt = (uint32_t)(tr & 2047ull);
+    const unsigned long long rec_off = tr >> 11;
+    const unsigned long long base_count = base >> kCountShift, base_samples = base & ((1ull << kCountShift) - 1ull);
+    for (uint32_t j = lane; j < cnt; j += 32u) {
+      if (rec_off + j >= a.max_frames) continue;   // flagged by the scan kernel
+      FrameRec fr = a.recs[rec_off + j];
+      fr.out_off += base_samples;
+      if (base_count + j < a.max_frames) a.frames[base_count + j] = fr;
+      else atomicOr(a.result + 2, 1ull);
     }
   }
 }
@@ -454,6 +507,11 @@ cudaError_t launch_scan(const ScanArgs &a, cudaStream_t stream) {
   if ((uint32_t)grid > a.n_tiles) grid = (int)a.n_tiles;
   if (grid < 1) grid = 1;
   scan_headers_kernel<<<grid, kScanThreads, 0, stream>>>(a);
+  tile_prefix_kernel<<<1, 1024, 0, stream>>>(a);
+  unsigned pg = (a.n_tiles + 7u) / 8u;
+  if (pg > (unsigned)sms * 8u) pg = (unsigned)sms * 8u;
+  if (pg < 1u) pg = 1u;
+  place_frames_kernel<<<pg, 256, 0, stream>>>(a);
   return cudaGetLastError();
 }
 

@@ -76,7 +76,10 @@ struct ScanArgs {
   unsigned long long stream_len;
   FrameRec *frames;
   unsigned long long max_frames;
-  unsigned long long *tile_status;  // [n_tiles] look-back words, zeroed
+  unsigned long long *tile_status;  // [n_tiles] frames << 38 | samples of the tile, then its exclusive prefix
+  unsigned long long *tile_recs;    // [n_tiles] (first record << 11) | records of the tile
+  FrameRec *recs;                   // [max_frames] the tiles' records in arrival order (sample offsets tile-relative)
+  unsigned long long *rec_cursor;   // zeroed
   unsigned int *ticket;             // zeroed
   unsigned long long *result;       // [0] n_frames, [1] total samples, [2] flags (1 = needs host walk)
   const uint16_t *crc_tables;

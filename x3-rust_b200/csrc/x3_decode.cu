@@ -283,7 +283,10 @@ __device__ __forceinline__ uint32_t load_be32_2aligned(const uint8_t *p) {
   return ((a & 0xff) << 24) | ((a >> 8) << 16) | ((b & 0xff) << 8) | (b >> 8);
 }
 
-__global__ void __launch_bounds__(256) crc_frames_kernel(const DecodeArgs a) {
+#ifndef X3_CRC_THREADS
+#define X3_CRC_THREADS 256   // 128 or 64 (more CTAs beside the decode kernel) were measured: the pair finishes later
+#endif
+__global__ void __launch_bounds__(X3_CRC_THREADS) crc_frames_kernel(const DecodeArgs a) {
   __shared__ uint16_t s_T[kCrcTableEntries];
   for (int i = threadIdx.x; i < kCrcTableEntries; i += blockDim.x) s_T[i] = a.crc_tables[i];
   __syncthreads();
@@ -528,10 +531,10 @@ cudaError_t launch_crc(const DecodeArgs &a, unsigned long long n_frames_hint, cu
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (n_frames_hint < 1) n_frames_hint = 1;
-  unsigned long long g = (n_frames_hint * 32ull + 255ull) / 256ull;  // one warp per frame
-  const unsigned long long cap = (unsigned long long)sms * 8ull;
+  unsigned long long g = (n_frames_hint * 32ull + X3_CRC_THREADS - 1ull) / X3_CRC_THREADS;  // one warp per frame
+  const unsigned long long cap = (unsigned long long)sms * (2048ull / X3_CRC_THREADS);
   if (g > cap) g = cap;
-  crc_frames_kernel<<<(unsigned)g, 256, 0, stream>>>(a);
+  crc_frames_kernel<<<(unsigned)g, X3_CRC_THREADS, 0, stream>>>(a);
   return cudaGetLastError();
 }
 

@@ -249,11 +249,14 @@ def main():
         nonlocal shard_sizes
         _, length, stats = dev.encode_tensor(pcm, params, out=stream)
         enc_ms = dev.last_kernel_ms()
+        # the only exchange: an NCCL all-gather of one int64 per rank, started as soon as the shard's size is known
+        # and left to run beside the decode of the rank's own shard
+        pending = sharding.exchange_sizes_begin(length, dist, device) if world > 1 else None
         _, ns, res, code = dev.decode_tensor(stream, length, params, out=dec)
         dec_ms = dev.last_kernel_ms()
         assert code == 0 and ns == n, (code, ns)
         if world > 1:
-            shard_sizes, _base = sharding.exchange_sizes(length, dist, device)   # the only exchange (NCCL all-gather)
+            shard_sizes, _base = sharding.exchange_sizes_end(pending)
         return length, enc_ms, dec_ms, stats
 
     def barrier():

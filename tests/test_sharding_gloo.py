@@ -24,6 +24,9 @@ def _worker(rank, world, port, n, tmpdir):
     s0, s1 = sharding.shard_frames(n, 10000, rank, world)
     stream, _ = oracle.encode(pcm[s0:s1])
     sizes, base = sharding.exchange_sizes(stream.size, dist)
+    pending = sharding.exchange_sizes_begin(stream.size, dist)      # the overlapped form bench.py uses
+    sizes2, base2 = sharding.exchange_sizes_end(pending)
+    assert sizes2 == sizes and base2 == base
     np.save(os.path.join(tmpdir, "shard%d.npy" % rank), stream)
     np.save(os.path.join(tmpdir, "meta%d.npy" % rank), np.array([s0, s1, base] + sizes, dtype=np.int64))
     dist.destroy_process_group()

@@ -44,3 +44,29 @@ def exchange_sizes(local_size: int, dist=None, device=None) -> Tuple[List[int], 
     dist.all_gather_into_tensor(sizes, mine)
     lst = [int(x) for x in sizes.tolist()]
     return lst, sum(lst[:rank])
+
+
+def exchange_sizes_begin(local_size: int, dist=None, device=None):
+    """Start the all-gather of exchange_sizes without waiting for it: the collective runs beside whatever the
+    rank does next (the decode of its own shard does not need the other ranks' sizes).  Returns a handle for
+    exchange_sizes_end."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return ([int(local_size)], None, None)
+    import torch
+    world = dist.get_world_size()
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    mine = torch.tensor([int(local_size)], dtype=torch.int64, device=device)
+    sizes = torch.zeros(world, dtype=torch.int64, device=device)
+    work = dist.all_gather_into_tensor(sizes, mine, async_op=True)
+    return (sizes, work, (dist, mine))
+
+
+def exchange_sizes_end(handle) -> Tuple[List[int], int]:
+    """Wait for exchange_sizes_begin's collective; returns (sizes, this rank's base offset)."""
+    sizes, work, ctx = handle
+    if work is None:
+        return sizes, 0
+    work.wait()
+    lst = [int(x) for x in sizes.tolist()]
+    return lst, sum(lst[:ctx[0].get_rank()])

@@ -583,13 +583,15 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const __grid
   }
 
   // ================================== workers ==================================
+  // samples of frame f: every frame is full except possibly the last (32-bit compare instead of 64-bit arithmetic)
+  const uint32_t last_f = a.n_frames - 1u;
+  const uint32_t last_n = (uint32_t)(a.n_samples - (unsigned long long)last_f * spf);
   if (tid == 0) s_misc[32] = atomicAdd(a.ticket, 1u);
   bar_workers();
   uint32_t f = s_misc[32];
   if (f < a.n_frames) {
     const unsigned long long s00 = (unsigned long long)f * spf;
-    const unsigned long long r0 = a.n_samples - s00;
-    const uint32_t n0 = r0 < spf ? (uint32_t)r0 : spf;
+    const uint32_t n0 = f == last_f ? last_n : spf;
     if (tid == 0) stage_frame_bulk(a.pcm, s00, n0, s_in, mbar);
     if (n0 & 7u) stage_tail_fast(a.pcm, s00, n0, s_in, tid);
   }
@@ -601,9 +603,7 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const __grid
 
   while (f != kNoFrame && f < a.n_frames) {
     uint32_t *s_words = s_img + par * img_words;
-    const unsigned long long s0 = (unsigned long long)f * spf;
-    const unsigned long long remn = a.n_samples - s0;
-    const uint32_t n = remn < spf ? (uint32_t)remn : spf;
+    const uint32_t n = f == last_f ? last_n : spf;
     const uint32_t nblk = n > 1 ? (n - 2u) / BL + 1u : 1u;  // <= 512
 
     if (n & 7u) bar_workers();  // the last frame's tail samples were stored by other threads
@@ -697,8 +697,7 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const __grid
     // the copy-out run
     if (f_next != kNoFrame) {
       const unsigned long long s1 = (unsigned long long)f_next * spf;
-      const unsigned long long r1 = a.n_samples - s1;
-      const uint32_t n1 = r1 < spf ? (uint32_t)r1 : spf;
+      const uint32_t n1 = f_next == last_f ? last_n : spf;
       if (tid == 0) stage_frame_bulk(a.pcm, s1, n1, s_in, mbar);
       if (n1 & 7u) stage_tail_fast(a.pcm, s1, n1, s_in, tid);
     }

@@ -245,19 +245,32 @@ def main():
 
     shard_sizes = [0] * world
 
+    # The device-pointer C ABI called directly (x3_encode_device / x3_decode_device on torch's current stream), with
+    # the argument objects built once: every microsecond of Python between two stream-synchronous calls is GPU idle
+    # time inside the timed region.  (x3-rust_b200.device.encode_tensor / decode_tensor wrap the same two calls.)
+    ps_dev = params.c_struct()
+    cur_stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p_pcm, p_stream, p_dec = C.c_void_p(pcm.data_ptr()), C.c_void_p(stream.data_ptr()), C.c_void_p(dec.data_ptr())
+    out_len, n_out = C.c_size_t(), C.c_size_t()
+    st_enc, res_dec = pkg._lib.x3_stats(), pkg._lib.x3_decode_result()
+    ms_enc, ms_dec = (C.c_float * 4)(), (C.c_float * 4)()
+    r_ps, r_len, r_st, r_n, r_res = C.byref(ps_dev), C.byref(out_len), C.byref(st_enc), C.byref(n_out), C.byref(res_dec)
+    r_me, r_md = C.byref(ms_enc), C.byref(ms_dec)
+
     def step():
         nonlocal shard_sizes
-        _, length, stats = dev.encode_tensor(pcm, params, out=stream)
-        enc_ms = dev.last_kernel_ms()
+        rc = L.x3_encode_device(p_pcm, n, r_ps, p_stream, bound, r_len, r_st, cur_stream)
+        L.x3_last_kernel_ms(r_me)
+        length = out_len.value
         # the only exchange: an NCCL all-gather of one int64 per rank, started as soon as the shard's size is known
         # and left to run beside the decode of the rank's own shard
         pending = sharding.exchange_sizes_begin(length, dist, device) if world > 1 else None
-        _, ns, res, code = dev.decode_tensor(stream, length, params, out=dec)
-        dec_ms = dev.last_kernel_ms()
-        assert code == 0 and ns == n, (code, ns)
+        code = L.x3_decode_device(p_stream, length, r_ps, p_dec, n, r_n, r_res, cur_stream)
+        L.x3_last_kernel_ms(r_md)
+        assert rc == 0 and code == 0 and n_out.value == n, (rc, code, n_out.value)
         if world > 1:
             shard_sizes, _base = sharding.exchange_sizes_end(pending)
-        return length, enc_ms, dec_ms, stats
+        return length, list(ms_enc), list(ms_dec), [int(v) for v in st_enc.samples_by_mode]
 
     def barrier():
         if world > 1:

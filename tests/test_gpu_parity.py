@@ -364,3 +364,30 @@ def test_decode_host_pipelined_pieces(pkg, dev, oracle, monkeypatch):
         out, res = pkg.decoder.decode_stream(s, p, max_samples=n + 20000)
         assert res.code == rc and res.frames == frames_ok and res.frame_errors == ferr, (i, res.code, rc)
         assert out.size == ref.size and np.array_equal(out, ref), i
+
+
+def test_decode_host_pipelined_equals_plain_path(pkg, oracle, monkeypatch):
+    """The pipelined and the plain host decode must agree on everything they report, also when the PCM buffer is
+    too small for the stream (a frame that does not fit stops the decode in both)."""
+    p = pkg.x3.Parameters.default()
+    n = 57 * 10000
+    pcm = oracle.synth(2, 0x58330002, 384000, 1000, n)
+    stream, _ = oracle.encode(pcm, threads=4)
+
+    def run(cap):
+        out, res = pkg.decoder.decode_stream(stream, p, max_samples=cap)
+        return res.code, res.frames, res.frame_errors, out.copy()
+
+    results = {}
+    for mode in ("pipe", "plain"):
+        if mode == "pipe":
+            monkeypatch.setenv("X3_DEC_PIPE_MIN_MB", "0")
+            monkeypatch.setenv("X3_DEC_PIPE_FIRST_KB", "8")
+        else:
+            monkeypatch.setenv("X3_DEC_PIPE_MIN_MB", "1000000")
+        results[mode] = [run(cap) for cap in (n, n - 1, n - 10000, 25000, 9999)]
+    for a, b in zip(results["pipe"], results["plain"]):
+        assert a[:3] == b[:3] and np.array_equal(a[3], b[3])
+    code, frames, ferr, out = results["plain"][0]
+    assert code == 0 and frames == 57 and np.array_equal(out, pcm)
+    assert results["plain"][2][1] == 56 and np.array_equal(results["plain"][2][3], pcm[:n - 10000])

@@ -364,7 +364,14 @@ __device__ __forceinline__ void bar_sync_all(uint32_t id) { asm volatile("bar.sy
 // bar.arrive orders this thread's prior shared-memory writes for the threads that bar.sync on the same barrier
 // (the PTX producer/consumer idiom); an explicit MEMBAR here cost ~600 cycles per frame
 __device__ __forceinline__ void bar_arrive_all(uint32_t id) { asm volatile("bar.arrive %0, 544;\n" ::"r"(id) : "memory"); }
-constexpr int kBarSize = 2, kBarCrc = 5, kBarOff = 8;  // + buffer index (0..NB-1)
+constexpr int kBarSize = 2, kBarCrc = 5;  // + buffer index (0..NB-1)
+// "Offset and header of the frame in ring slot q are ready" is an mbarrier per slot (one arrival by the control warp
+// per use of the slot, the workers wait on the phase parity of that use): unlike a named barrier it does not make
+// the sixteen worker warps meet, so they run from the CRC slices into the copy-out and the next frame's measure
+// phase on their own.
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(mbar) : "memory");
+}
 
 // payload image (16-byte aligned in shared memory) -> dst (2-byte aligned global address), 512 worker threads.
 // Body in 16-byte stores; the shared-memory side is read at a 2- or 4-byte skew and realigned with PRMT.
@@ -478,6 +485,7 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const __grid
   uint32_t *s_V = reinterpret_cast<uint32_t *>(p);                p += NB * kMaxSlices * 4;
   uint32_t *s_misc = reinterpret_cast<uint32_t *>(p);
   const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(s_misc + 80);  // 8 bytes: the frame stager's mbarrier
+  const uint32_t mbar_off = mbar + 8u;                                    // NB x 8 bytes: "offset ready" per ring slot
   // s_misc: [0..16) warp totals, [32] next ticket, [40..46) stats of short blocks,
   //         per parity q at [48+8q ..): +0 frame, +1 samples, +2 payload_len, +4,+5 byte offset, +6 fits
 
@@ -487,7 +495,10 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const __grid
 
   for (int i = tid; i < kCrcBankEntries2; i += NTF) s_crcT[i] = a.crc_tables[i];
   if (tid < 6) s_misc[40 + tid] = 0;
-  if (tid == 0) mbar_init(mbar, 1);
+  if (tid == 0) {
+    mbar_init(mbar, 1);
+    for (uint32_t q = 0; q < NB; q++) mbar_init(mbar_off + 8u * q, 1);
+  }
   __syncthreads();
   // Frames are handed out by an atomic ticket, LATE: a CTA draws its next frame only when it has finished packing
   // the current one, so that a ticketed frame publishes its size within about one measure phase.  (Drawing the
@@ -566,7 +577,7 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const __grid
         reinterpret_cast<uint16_t *>(a.out + excl)[lane] = (uint16_t)(((v & 0xff) << 8) | (v >> 8));
       }
       __syncwarp();
-      bar_arrive_all(kBarOff + par);
+      if (lane == 0) mbar_arrive(mbar_off + 8u * par);
       X3_T(4)
 #ifdef X3_ENC_TIMING
       cframes++;
@@ -684,6 +695,21 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const __grid
       // the frame's last word is completed by nobody: zero it for the tails that are ORed into it (and for the padding)
       if (total_bits & 31u) s_words[total_bits >> 5] = 0u;
     }
+    // ---- the oldest frame in the ring goes out now, before barrier (D): a warp that is done packing copies its share
+    // instead of waiting for the slowest one.  (Its offset has had NB-1 frame times to arrive; the slot is written
+    // again only by the next frame's pack, after that frame's barrier (B).) ----
+    if (it >= NB - 1) {
+      const uint32_t q = par + 1u == NB ? 0u : par + 1u;  // the buffer the next frame will reuse
+      mbar_wait(mbar_off + 8u * q, ((it - (NB - 1u)) / NB) & 1u);   // frame it-(NB-1) of this CTA was the slot's use number (it-(NB-1))/NB
+      X3_T(9)
+      const uint32_t *info = s_misc + 48 + 8 * q;
+      const uint32_t L = info[2];  // payload length (stays valid until this buffer's next measure phase)
+      if (info[6]) {
+        const unsigned long long off = (unsigned long long)info[4] | ((unsigned long long)info[5] << 32);
+        copy_payload_out(a.out + off + kFrameHeaderLen, s_img + q * img_words, L, tid);
+      }
+      X3_T(10)
+    }
     X3_T(4)
     bar_workers();  // (D) every plain store done
     X3_T(5)
@@ -731,19 +757,6 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const __grid
     bar_arrive_all(kBarCrc + par);  // -> control: slice CRCs and image complete
     X3_T(8)
 
-    // ---- the oldest frame in the ring goes out now: its offset has had NB-1 frame times to arrive ----
-    if (it >= NB - 1) {
-      const uint32_t q = par + 1u == NB ? 0u : par + 1u;  // the buffer the next frame will reuse
-      bar_sync_all(kBarOff + q);
-      X3_T(9)
-      const uint32_t *info = s_misc + 48 + 8 * q;
-      const uint32_t L = info[2];  // payload length (stays valid until this buffer's next measure phase)
-      if (info[6]) {
-        const unsigned long long off = (unsigned long long)info[4] | ((unsigned long long)info[5] << 32);
-        copy_payload_out(a.out + off + kFrameHeaderLen, s_img + q * img_words, L, tid);
-      }
-      X3_T(10)
-    }
     f = f_next;
     it++;
     par = par + 1u == NB ? 0u : par + 1u;
@@ -764,7 +777,7 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const __grid
     const uint32_t pending = it < NB - 1 ? it : NB - 1;
     uint32_t q = (par + NB - pending) % NB;
     for (uint32_t d = 0; d < pending; d++) {
-      bar_sync_all(kBarOff + q);
+      mbar_wait(mbar_off + 8u * q, ((it - pending + d) / NB) & 1u);
       const uint32_t *info = s_misc + 48 + 8 * q;
       const uint32_t L = info[2];  // payload length (stays valid until this buffer's next measure phase)
       if (info[6]) {

@@ -63,6 +63,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz, self.stop_flag = index, [], set(), None, False
+        self.period = float(os.environ.get("X3_BENCH_CLOCK_PERIOD_MS", "4")) * 1e-3
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -82,19 +83,26 @@ class ClockSampler(threading.Thread):
             ("nvmlClocksThrottleReasonHwSlowdown", "hw_slowdown"), ("nvmlClocksThrottleReasonHwThermalSlowdown", "hw_thermal_slowdown"),
             ("nvmlClocksThrottleReasonSwThermalSlowdown", "sw_thermal_slowdown"), ("nvmlClocksThrottleReasonSwPowerCap", "sw_power_cap"),
         ) if hasattr(nv, k)}
+        self.names = names
         while not self.stop_flag:
+            self.sample_once()
+            time.sleep(self.period)
+
+    def sample_once(self):
+        nv = self.nv
+        if nv is None:
+            return
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
             except Exception:
-                pass
-            time.sleep(0.004)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in getattr(self, "names", {}).items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
 
     def summary(self):
         s = sorted(self.samples)
@@ -306,6 +314,7 @@ def main():
     value = n_total / (dt_ms * 1e-3) / 1e6
 
     # ---- e2e: the host-pointer C ABI, pinned host buffers, copies inside the timed region ----
+    sampler.period = 0.05   # a step is ~100 ms here: a coarser sampling period is enough
     e2e = None
     if not args.no_e2e:
         h_pcm = torch.empty(n, dtype=torch.int16).pin_memory()

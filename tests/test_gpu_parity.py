@@ -391,3 +391,23 @@ def test_decode_host_pipelined_equals_plain_path(pkg, oracle, monkeypatch):
     code, frames, ferr, out = results["plain"][0]
     assert code == 0 and frames == 57 and np.array_equal(out, pcm)
     assert results["plain"][2][1] == 56 and np.array_equal(results["plain"][2][3], pcm[:n - 10000])
+
+
+@pytest.mark.parametrize("kind,seed", [(2, 0x58330002), (4, 0x58330004)])
+def test_full_size_c2_c4_bytes_match_oracle(pkg, dev, oracle, kind, seed):
+    """BASELINE configs C2 / C4 at full size (1 h at 384 kHz = 1 382 400 000 samples): every byte of the GPU's frame
+    stream equals the oracle's, the mode statistics agree, and the GPU decode returns the input bit for bit."""
+    import torch
+    n = 1382400000
+    p = pkg.x3.Parameters.default()
+    pcm = dev.synth(kind, seed, 384000, 0, n)
+    out, length, stats = dev.encode_tensor(pcm, p)
+    host_pcm = pcm.cpu().numpy()
+    ref, rstats = oracle.encode(host_pcm, threads=os.cpu_count() or 8)
+    assert length == ref.size and stats == rstats
+    got = out[:length].cpu().numpy()
+    assert np.array_equal(got, ref)
+    del got, ref, host_pcm
+    dec, ns, res, code = dev.decode_tensor(out, length, p, max_samples=n)
+    assert code == 0 and ns == n and res.frames == 138240 and not res.used_host_walk
+    assert torch.equal(dec[:n], pcm)

@@ -411,3 +411,18 @@ def test_full_size_c2_c4_bytes_match_oracle(pkg, dev, oracle, kind, seed):
     dec, ns, res, code = dev.decode_tensor(out, length, p, max_samples=n)
     assert code == 0 and ns == n and res.frames == 138240 and not res.used_host_walk
     assert torch.equal(dec[:n], pcm)
+
+
+@pytest.mark.parametrize("file_index", [0, 511, 1023])
+def test_c5_files_match_oracle(pkg, dev, oracle, file_index):
+    """BASELINE config C5 (1024 files of 10 min at 96 kHz): files 0, 511 and 1023 in full -- GPU frame bytes equal
+    the oracle's, the decode returns the input (the subset the CPU oracle checks)."""
+    import torch
+    n = 57600000
+    p = pkg.x3.Parameters.default()
+    pcm = dev.synth(2, 0x58330005 + file_index, 96000, 0, n)
+    out, length, stats = dev.encode_tensor(pcm, p)
+    ref, rstats = oracle.encode(pcm.cpu().numpy(), threads=os.cpu_count() or 8)
+    assert length == ref.size and stats == rstats and np.array_equal(out[:length].cpu().numpy(), ref)
+    dec, ns, res, code = dev.decode_tensor(out, length, p, max_samples=n)
+    assert code == 0 and ns == n and res.frames == 5760 and torch.equal(dec[:n], pcm)

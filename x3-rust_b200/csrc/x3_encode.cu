@@ -1,17 +1,20 @@
-// x3_encode.cu -- frame encoder kernel for sm_100a.
+// x3_encode.cu -- frame encoder kernels for sm_100a.
 //
-// One CTA encodes one frame at a time (persistent CTAs, frames handed out by an atomic ticket):
-//   1. the frame's PCM is staged in shared memory with 16-byte cp.async copies;
+// Two kernels with the same phases (persistent CTAs, one frame per CTA at a time, frames handed out by an atomic
+// ticket): encode_frames_generic_kernel for any Parameters the API accepts, and encode_frames_fast_kernel
+// (further down, the one that is tuned) for Parameters::default() with at most 512 blocks per frame.
+//   1. the frame's PCM is staged in shared memory (generic: 16-byte cp.async; fast: one TMA bulk copy on an mbarrier);
 //   2. one thread per block: first difference, zig-zag fold, max -> mode (encoder.rs:304-314), bit length;
 //   3. CTA-wide exclusive scan of the bit lengths -> bit offset of every block inside the frame;
 //   4. each thread packs its block MSB-first straight into its final position in a shared-memory byte
-//      image (x3_enc_core.cuh: one writer per word, no atomics);
-//   5. CRC-16 of the payload: 16-byte chunks in parallel, combined by one warp (Horner + shuffle tree with
-//      multiply-by-x^n tables), header built (encoder.rs:122-162);
-//   6. decoupled look-back over the frame sizes gives the frame's byte offset in the output stream;
+//      image (x3_enc_core.cuh);
+//   5. CRC-16 of the payload: 16-byte chunks in parallel, combined with multiply-by-x^n tables (shuffle tree +
+//      Horner), header built (encoder.rs:122-162);
+//   6. the frame's byte offset in the output stream: a prefix over the frame sizes (generic: decoupled look-back
+//      per CTA; fast: a scanner CTA that turns published sizes into prefixes);
 //   7. the image is copied to global memory with coalesced stores.
 // HBM traffic is exactly the algorithmic figure: every PCM byte read once, every output byte written once
-// (plus 8 bytes of look-back status per frame).
+// (plus 8 bytes of status per frame).
 #include <cuda_runtime.h>
 
 #include "x3_enc_core.cuh"
@@ -296,15 +299,17 @@ __global__ void __launch_bounds__(NT, 1) encode_frames_generic_kernel(const Enco
 // Fast kernel: Parameters::default() and at most 512 blocks per frame.
 //
 // 16 worker warps (one thread per block) and 1 control warp that runs ASYNCHRONOUSLY: the two sides meet only
-// through named barriers used as producer/consumer signals (bar.arrive / bar.sync), and the frame image is
-// double buffered, so a frame's byte offset (which needs every earlier frame's size: decoupled look-back)
-// has a whole frame time to arrive before anybody waits for it.
+// through named barriers used as producer/consumer signals (bar.arrive / bar.sync) and one mbarrier per ring slot,
+// and the frame image lives in a ring of NB = 3 buffers, so a frame's byte offset (which needs every earlier frame's
+// size) has two frame times to arrive before anybody waits for it.  CTA 0 is the scanner (scanner_role).
 //
-//   workers, frame i:  stage samples -> measure + CTA scan -> [size_ready] -> prefetch next frame, pack into
-//                      image[i&1] (plain stores + one atomicOr per unaligned block) -> per-warp CRC slices
-//                      -> [crc_ready] -> wait [off_ready of frame i-1] and copy frame i-1's payload out.
-//   control, frame i:  wait [size_ready] -> publish size, look back -> wait [crc_ready] -> fold the slice CRCs,
-//                      build and write the 20-byte header (encoder.rs:122-162) -> [off_ready].
+//   workers, frame i:  wait for the staged samples (mbarrier of the TMA copy) -> measure + CTA scan -> publish the
+//                      size, [size_ready(i)] -> pack into image[i % NB] (plain stores; a block's last partial word
+//                      stays in a register) -> wait [off_ready(i-2)], copy frame i-2's payload out -> barrier ->
+//                      OR the partial words in -> barrier -> start the TMA copy of the next frame -> per-warp CRC
+//                      slices -> [crc_ready(i)].
+//   control:           on [size_ready(i)]: finish frame i-1 -- poll its prefix (there by now), wait [crc_ready(i-1)],
+//                      fold the slice CRCs, build and write the 20-byte header (encoder.rs:122-162), [off_ready(i-1)].
 // ------------------------------------------------------------------------------------------------
 constexpr int NTF = kEncFastThreads;      // 544
 constexpr int NWW = 16;                   // worker warps

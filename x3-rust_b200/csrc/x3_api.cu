@@ -705,6 +705,7 @@ int decode_device_impl(const uint8_t *d_frames, size_t len, const x3_params *p, 
   da.max_frames = max_frames;
   da.frame_status = reinterpret_cast<int *>(ws + o_fstat);
   da.crc_status = reinterpret_cast<int *>(ws + o_cstat);
+  da.one = 1u;
   da.result = reinterpret_cast<unsigned long long *>(ws + o_dres);
   da.crc_tables = ds->crc_dev;
 

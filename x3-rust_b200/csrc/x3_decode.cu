@@ -377,6 +377,7 @@ struct RingReader {
   uint32_t pos0, pos;        // bit positions relative to chunk 0: payload start, current
   uint32_t s;                // pos & 31
   uint32_t rb;               // shared-window byte address of the ring
+  uint32_t one;              // 1 (DecodeArgs::one)
   uint32_t A, B, C, D;       // big-endian words w, w+1, w+2, w+3 with w = pos >> 5
 
   __device__ __forceinline__ void issue_to(uint32_t want) {
@@ -430,7 +431,21 @@ struct RingReader {
 #ifndef X3_DEC_ASMLD
 #define X3_DEC_ASMLD 0  // 1, 2: ld.shared from a precomputed 32-bit address (one instruction fewer, measured 2 % slower)
 #endif
-#if X3_DEC_ASMLD == 3
+#if X3_DEC_ASMLD == 4
+    // the window shifts by one word as four predicated IMADs (x * one + 0): the FMA pipe is idle, the ALU pipe -- where
+    // the four selects would go -- is this kernel's top limiter
+    const uint32_t nd4 = bswap32(ring[((pos >> 5) + 3u) & 31u]);
+    asm("{\n"
+        ".reg .pred p;\n"
+        "setp.gt.u32 p, %4, 31;\n"
+        "@p mad.lo.u32 %0, %1, %5, 0;\n"
+        "@p mad.lo.u32 %1, %2, %5, 0;\n"
+        "@p mad.lo.u32 %2, %3, %5, 0;\n"
+        "@p mad.lo.u32 %3, %6, %5, 0;\n"
+        "}\n"
+        : "+r"(A), "+r"(B), "+r"(C), "+r"(D)
+        : "r"(s2), "r"(one), "r"(nd4));
+#elif X3_DEC_ASMLD == 3
     // load only in the lanes that cross a word boundary: fewer lanes per shared-memory access, fewer bank conflicts
     // (the ring positions of the 32 lanes are unrelated, so every active lane is a potential conflict)
     A = cross ? B : A;
@@ -489,6 +504,7 @@ __global__ void __launch_bounds__(kDecThreads, X3_DEC_MINBLOCKS) decode_frames_k
         int r = kDecRetryExact;
         if (dflt && frame_fast_eligible(fr.samples, fr.payload_len, (uintptr_t)pl, (uintptr_t)out)) {
           RingReader rd;
+          rd.one = a.one;
           rd.start(pl, stream_end, s_ring + tid * kRingWords);
           r = decode_frame_fast(rd, fr.payload_len, out, fr.samples, s_stage + tid, (uint32_t)kDecThreads, s_inv, s_par);
           cp_async_wait_all();

@@ -65,6 +65,7 @@ struct DecodeArgs {
   int *crc_status;                     // [max_frames] verdict of crc_frames_kernel (runs concurrently with the decode;
                                        // a frame's status is crc_status if that is an error, else frame_status)
   unsigned long long *result;          // [0] first bad frame of either kernel (init ~0), [1] unused
+  uint32_t one;                        // 1, opaque to the compiler: x * one + 0 is a register move on the FMA pipe
   const uint16_t *crc_tables;
 };
 

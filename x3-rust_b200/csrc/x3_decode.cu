@@ -429,7 +429,7 @@ struct RingReader {
     // word (pos >> 5) + 3 of the ring, i.e. byte ((pos >> 3) + 12) & 124; only used when crossing, the slot is valid
     // either way
 #ifndef X3_DEC_ASMLD
-#define X3_DEC_ASMLD 0  // 1, 2: ld.shared from a precomputed 32-bit address (one instruction fewer, measured 2 % slower)
+#define X3_DEC_ASMLD 4  // 0: selects; 1, 2: ld.shared from a precomputed 32-bit address (measured 2 % slower); 3: predicated load; 4: see below
 #endif
 #if X3_DEC_ASMLD == 4
     // the window shifts by one word as four predicated IMADs (x * one + 0): the FMA pipe is idle, the ALU pipe -- where

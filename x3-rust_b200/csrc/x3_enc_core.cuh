@@ -313,9 +313,18 @@ struct FastSink {
     cnt += n;
   }
   X3_HD void flush() {
+    const uint32_t w = bswap32((uint32_t)(acc >> (cnt & 31u)));   // cnt in [32,63]: acc >> (cnt - 32)
+#if defined(__CUDA_ARCH__)
+    // one compare; the store and the pointer step are both predicated on it
+    asm volatile("{ .reg .pred p; setp.ge.u32 p, %1, 32; @p st.shared.u32 [%0], %2; @p add.u32 %0, %0, 4; }"
+                 : "+r"(dst)
+                 : "r"(cnt), "r"(w)
+                 : "memory");
+#else
     const uint32_t full = cnt >> 5;         // 0 or 1
-    sm_store_if(full != 0u, dst, bswap32((uint32_t)(acc >> (cnt & 31u))));   // cnt in [32,63]: acc >> (cnt - 32)
+    sm_store_if(full != 0u, dst, w);
     dst = sm_advance(dst, full);
+#endif
     cnt &= 31u;
   }
   X3_HD uint32_t finish_tail() {            // the word at dst, valid if cnt != 0 afterwards

@@ -256,6 +256,35 @@ int sim_encode(const int16_t *pcm, size_t n, const uint32_t *params /*bl,bpf,c0,
   return 0;
 }
 
+// The decoder's table bank against the reference's definition (decoder.rs:157-191, x3.rs:200-252): for every zero
+// run z the 32-bit peek can see and every suffix r whose terminator bit is set, q = z*2^nbk + r must map to
+// INV_RICE_CODE[r + level*(z-1)] when that index is inside the code's table (inv_len 16 / 26 / 60) and must be
+// >= inv_q_end otherwise; q must be monotone in the index.  Returns 0 when everything holds, else a failure code.
+int sim_inv_table_check() {
+  const int inv_len[4] = {0, 16, 26, 60};
+  for (int f = 1; f <= 3; f++) {
+    const RiceBlockPar bp = rice_block_par((uint32_t)f);
+    const int nbk = (int)bp.nbk, level = 1 << (nbk - 1);
+    if (bp.sh != 32u - bp.nbk || bp.q_end != inv_q_end((uint32_t)f)) return 10 + f;
+    if (bp.tab_off != (uint32_t)((f - 1) * kInvTabLen + kInvPad)) return 20 + f;
+    int last_i = -1;
+    for (int z = 0; z <= 31; z++)
+      for (int r = level; r < (1 << nbk); r++) {
+        const int q = (z << nbk) + r, i = r + level * (z - 1);
+        if (q + kInvPad >= kInvTabLen) return 30 + f;          // must stay inside the table
+        if (i <= last_i) return 40 + f;                        // q order == index order
+        last_i = i;
+        const bool valid = i >= 0 && i < inv_len[f];
+        if (valid != ((uint32_t)q < bp.q_end)) return 50 + f;
+        if (valid && (int)inv_tab_entry(f, q + kInvPad) != unfold((uint32_t)i)) return 60 + f;
+      }
+    for (int q = -kInvPad; q < 0; q++)                          // the pad an all-zero peek lands in
+      if (inv_tab_entry(f, q + kInvPad) != 0) return 70 + f;
+  }
+  if (rice_block_par(0).q_end != 1u) return 80;                 // the opaque constant 1 of X3_CUM_ADD
+  return 0;
+}
+
 uint32_t sim_crc(const uint8_t *data, uint32_t len) {  // len even
   std::vector<uint32_t> w((len + 19) / 4 + 4, 0);
   memcpy(w.data(), data, len);

@@ -63,6 +63,11 @@ def signals(oracle):
     return sig
 
 
+def test_decoder_tables_match_reference_definition(sim):
+    """inverse-fold table bank, q_end thresholds and per-ftype LUT of the GPU decoder vs decoder.rs / x3.rs"""
+    assert sim.sim_inv_table_check() == 0
+
+
 def test_sim_crc_matches_serial(sim, oracle):
     rng = np.random.default_rng(1)
     for n in [2, 4, 6, 14, 16, 18, 30, 32, 34, 510, 512, 514, 1022, 4096, 5000, 20376, 24576]:

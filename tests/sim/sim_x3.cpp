@@ -13,6 +13,7 @@
 #include "../../x3-rust_b200/csrc/x3_crc_host.h"
 #include "../../x3-rust_b200/csrc/x3_dec_core.cuh"
 #include "../../x3-rust_b200/csrc/x3_enc_core.cuh"
+#include "../../x3-rust_b200/csrc/x3_enc_strip.cuh"
 
 using namespace x3;
 
@@ -152,6 +153,136 @@ size_t sim_encode_frame_fast(const int16_t *pcm, uint32_t n, const CodecParams &
   return 20 + payload_len;
 }
 
+
+// one frame, mirroring encode_frames_strip_kernel: 128 simulated threads, one strip of four blocks each; local pack in
+// place in 176-byte rows, scan, relocation into a window aligned like the stream modulo 16 bytes (gpay = stream offset
+// of the payload), windowed rounds, sliced CRC over 32-byte chunks.  win_bytes = window size (multiple of 1024).
+size_t sim_encode_frame_strip(const int16_t *pcm, uint32_t n, const CodecParams &P, unsigned long long gpay,
+                              uint32_t win_bytes, uint8_t *out, uint64_t stats[6]) {
+  const uint16_t *t2 = T() + kCrcTableEntries;
+  const uint32_t nblk = n > 1 ? (n - 2u) / 20u + 1u : 1u;
+  std::vector<uint32_t> rows((kStripMaxRows + 1) * kRowWords, 0x5a5a5a5au);
+  uint32_t s_next[4][4];
+  memset(s_next, 0x6b, sizeof s_next);
+  // stage_rows: chunk c of warp w -> byte 16 * (c + c / 10) of the warp's rows (the kernel's multiply-shift division)
+  for (uint32_t w = 0; w < 4; w++) {
+    const uint32_t w0 = w * 32u * kStripSamples;
+    const uint32_t avail = n > w0 ? n - w0 : 0u, chunks = avail >> 3;
+    unsigned char *dst = reinterpret_cast<unsigned char *>(rows.data() + w * 32u * kRowWords);
+    for (uint32_t c = 0; c < 320u && c < chunks; c++) {
+      if (((c * 205u) >> 11) != c / 10u) return 0;
+      memcpy(dst + 16u * (c + ((c * 205u) >> 11)), pcm + w0 + 8u * c, 16);
+    }
+    if (chunks > 320u) memcpy(s_next[w], pcm + w0 + 2560u, 16);
+    if (avail < 32u * kStripSamples + 8u)
+      for (uint32_t i = chunks << 3; i < avail && i < 32u * kStripSamples + 8u; i++) {
+        if (i < 32u * kStripSamples)
+          reinterpret_cast<int16_t *>(rows.data() + (w * 32u + i / kStripSamples) * kRowWords)[i % kStripSamples] = pcm[w0 + i];
+        else
+          reinterpret_cast<int16_t *>(s_next[w])[i - 32u * kStripSamples] = pcm[w0 + i];
+      }
+  }
+  uint32_t nxt[128], Tb[128], O[128];
+  for (uint32_t t = 0; t < 128; t++) nxt[t] = (t & 31u) == 31u ? s_next[t >> 5][0] : rows[(t + 1) * kRowWords];
+  uint32_t short_stats[6] = {0, 0, 0, 0, 0, 0};
+  unsigned long long stat_acc_sum[6] = {0, 0, 0, 0, 0, 0};
+  for (uint32_t t = 0; t < 128; t++) {
+    uint32_t *row = rows.data() + t * kRowWords;
+    Tb[t] = 0;
+    const uint32_t b0 = kStripBlocks * t;
+    if (b0 >= nblk) continue;
+    if (b0 + kStripBlocks <= nblk && n >= kStripSamples * (t + 1u)) {
+      const bool full = n > kStripSamples * (t + 1u);
+      unsigned long long acc = 0;
+      uint32_t s19 = 0;
+      Tb[t] = strip_pack_fast(row, nxt[t], full, t == 0, -1, acc, s19);
+      if (!full) short_stats[s19] += 19u;
+      for (int m = 0; m < 6; m++) stat_acc_sum[m] += ((acc >> (10 * m)) & 1023u) * 20u;
+    } else {
+      Tb[t] = strip_pack_generic(row, nxt[t], t, n, nblk, P, short_stats);
+    }
+  }
+  for (int m = 0; m < 6; m++) stats[m] += stat_acc_sum[m] + short_stats[m];
+  uint32_t total_bits = 0;
+  for (uint32_t t = 0; t < 128; t++) { O[t] = total_bits; total_bits += Tb[t]; }
+  const uint32_t payload_len = payload_bytes(total_bits);
+  const uint32_t a_off = (uint32_t)(gpay & 15u), end_bytes = a_off + payload_len;
+  const uint32_t win_words = win_bytes / 4u, win_chunks = win_bytes / 32u;
+  const uint32_t nrounds = (end_bytes + win_bytes - 1u) / win_bytes, nch = end_bytes >> 5;
+  std::vector<uint32_t> win(win_words + 8u);
+  std::vector<uint32_t> V(64, 0u);
+  std::vector<uint8_t> image(end_bytes + 64u, 0xEE);   // window-space bytes as written to the stream
+  for (uint32_t r = 0; r < nrounds; r++) {
+    std::fill(win.begin(), win.end(), 0xdeadbeefu);     // stale data of the previous round / frame
+    const int32_t wbit0 = (int32_t)(8u * r * win_bytes);
+    if (r == 0) for (uint32_t k = 0; k < (a_off >> 2); k++) win[k] = 0u;
+    const int32_t zt = (int32_t)(8u * a_off + total_bits) - wbit0;
+    if (zt >= 0 && (zt >> 5) < (int32_t)win_words) { win[zt >> 5] = 0u; win[(zt >> 5) + 1] = 0u; }
+    uint32_t tail[128];
+    int32_t tail_idx[128];
+    for (uint32_t t = 0; t < 128; t++)
+      strip_relocate(rows.data() + t * kRowWords, Tb[t], (int32_t)(8u * a_off + O[t]) - wbit0, win.data(), win_words, tail[t], tail_idx[t]);
+    for (uint32_t t = 0; t < 128; t++)
+      if (tail_idx[t] >= 0) win[tail_idx[t]] |= tail[t];
+    const uint32_t vb0 = r == 0 ? a_off : 0u;
+    const uint32_t vb1 = end_bytes - r * win_bytes < win_bytes ? end_bytes - r * win_bytes : win_bytes;
+    memcpy(image.data() + r * win_bytes + vb0, reinterpret_cast<const uint8_t *>(win.data()) + vb0, vb1 - vb0);
+    const uint32_t c_lo = r * win_chunks, c_hi = nch < (r + 1u) * win_chunks ? nch : (r + 1u) * win_chunks;
+    if (c_hi > c_lo) {
+      const uint32_t j_lo = (nch - c_hi) >> 5, j_hi = (nch - 1u - c_lo) >> 5;
+      for (uint32_t j = j_lo; j <= j_hi; j++) {
+        uint32_t h[32];
+        for (uint32_t lane = 0; lane < 32; lane++) {
+          const uint32_t e = 32u * j + lane;
+          h[lane] = 0;
+          if (e >= nch) continue;
+          const uint32_t c = nch - 1u - e;
+          if (c < c_lo || c >= c_hi) continue;
+          uint32_t q[8];
+          memcpy(q, win.data() + 8u * (c - c_lo), 32);
+          if (c == 0) q[a_off >> 2] ^= 0xffffu << (8u * (a_off & 2u));
+          uint32_t s = 0;
+          for (int w = 0; w < 8; w++) s = crc16_word_sw(t2, s, q[w]);
+          h[lane] = s;
+        }
+        const int tb[5] = {8, 10, 12, 14, 4};
+        for (int k = 0; k < 5; k++) {
+          uint32_t o[32];
+          for (int lane = 0; lane < 32; lane++) o[lane] = lane + (1 << k) < 32 ? h[lane + (1 << k)] : h[lane];
+          for (int lane = 0; lane < 32; lane++)
+            h[lane] ^= (uint32_t)t2[tb[k] * 256 + ((o[lane] >> 8) & 0xffu)] ^ (uint32_t)t2[(tb[k] + 1) * 256 + (o[lane] & 0xffu)];
+        }
+        V[j] ^= h[0] & 0xffffu;
+      }
+    }
+    if (r == nrounds - 1u) {
+      const uint32_t nsl = (nch + 31u) >> 5;
+      uint32_t s = 0;
+      auto mul4096 = [&](uint32_t x) { return (uint32_t)t2[4 * 256 + ((x >> 8) & 0xffu)] ^ (uint32_t)t2[5 * 256 + (x & 0xffu)]; };
+      for (int j = (int)nsl - 1; j >= 0; j--) s = mul4096(mul4096(s)) ^ V[j];
+      const uint32_t base = r * win_bytes;
+      uint32_t pos = 32u * nch;
+      while (pos + 4u <= end_bytes) {
+        uint32_t w = win[(pos - base) >> 2];
+        if (nch == 0 && (pos >> 2) == (a_off >> 2)) w ^= 0xffffu << (8u * (a_off & 2u));
+        s = crc16_word_sw(t2, s, w);
+        pos += 4u;
+      }
+      if (pos < end_bytes) {
+        uint32_t hv = win[(pos - base) >> 2] & 0xffffu;
+        if (nch == 0 && (pos >> 2) == (a_off >> 2) && (a_off & 2u) == 0u) hv ^= 0xffffu;
+        s = crc16_half_sw(t2, s, hv);
+      }
+      const uint32_t hc = header_crc_sw(t2, 1u, n, payload_len), crc = bswap16(s);
+      uint32_t hdr[5] = {bswap32((kFrameKey << 16) | 0x0101u), bswap32(((n & 0xffffu) << 16) | (payload_len & 0xffffu)), 0u, 0u,
+                         bswap32((hc << 16) | crc)};
+      memcpy(out, hdr, 20);
+    }
+  }
+  memcpy(out + 20, image.data() + a_off, payload_len);
+  return 20 + payload_len;
+}
+
 // one frame, mirroring encode_frames_generic_kernel (single CTA, NT simulated threads)
 size_t sim_encode_frame(const int16_t *pcm, uint32_t n, const CodecParams &P, bool fast_kernel, bool last_frame,
                         uint8_t *out, uint64_t stats[6]) {
@@ -241,13 +372,20 @@ int sim_encode(const int16_t *pcm, size_t n, const uint32_t *params /*bl,bpf,c0,
   P.block_len = params[0];
   P.spf = params[0] * params[1];
   for (int k = 0; k < 3; k++) { P.codes[k] = params[2 + k]; P.thresholds[k] = params[5 + k]; }
-  const bool fast = params_are_default(P) && params[1] <= 512 && !force_generic;
+  // force_generic: low 4 bits 0 = strip kernel, 1 = generic kernel, 2 = round-1 fast kernel; bits 4..7 = (stream base
+  // address mod 16) / 2 and bits 8.. = window bytes / 1024 (0 = 7) for the strip kernel
+  const int mode = force_generic & 15;
+  const bool fast = params_are_default(P) && params[1] <= 512 && mode != 1 && (P.spf % 8u) == 0u;
+  const unsigned long long base_mod = 2ull * ((force_generic >> 4) & 7);
+  const uint32_t win_bytes = 1024u * ((force_generic >> 8) ? (uint32_t)(force_generic >> 8) : 7u);
   size_t pos = 0;
   for (size_t s0 = 0; s0 < n; s0 += P.spf) {
     const uint32_t fn = (uint32_t)((n - s0) < P.spf ? (n - s0) : P.spf);
     std::vector<uint8_t> tmp(64 + 2 * (size_t)fn * 9);
-    const size_t L = fast ? sim_encode_frame_fast(pcm + s0, fn, P, s0 + fn >= n, tmp.data(), stats)
-                          : sim_encode_frame(pcm + s0, fn, P, false, s0 + fn >= n, tmp.data(), stats);
+    const size_t L = !fast ? sim_encode_frame(pcm + s0, fn, P, false, s0 + fn >= n, tmp.data(), stats)
+                     : mode == 2 ? sim_encode_frame_fast(pcm + s0, fn, P, s0 + fn >= n, tmp.data(), stats)
+                                 : sim_encode_frame_strip(pcm + s0, fn, P, base_mod + pos + 20u, win_bytes, tmp.data(), stats);
+    if (L == 0) return -200;
     if (pos + L > cap) return -15;
     memcpy(out + pos, tmp.data(), L);
     pos += L;

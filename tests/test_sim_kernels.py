@@ -16,7 +16,7 @@ SO = os.path.join(SIM_DIR, "libx3sim.so")
 def sim():
     src = os.path.join(SIM_DIR, "sim_x3.cpp")
     deps = [src] + [os.path.join(ROOT, "x3-rust_b200", "csrc", f) for f in
-                    ("x3_common.cuh", "x3_enc_core.cuh", "x3_dec_core.cuh", "x3_crc_host.h")]
+                    ("x3_common.cuh", "x3_enc_core.cuh", "x3_enc_strip.cuh", "x3_dec_core.cuh", "x3_crc_host.h")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-x", "c++", "-fPIC", "-shared", "-Wall",
                                "-Wno-unknown-pragmas", "-o", SO, src])
@@ -82,7 +82,9 @@ def test_sim_encode_golden(sim, golden):
         assert list(out) == g["expected"], name
 
 
-@pytest.mark.parametrize("force_generic", [0, 1])
+# 0: strip kernel (7 KiB window, 16-byte aligned stream base); 1: generic kernel; 2: round-1 fast kernel;
+# 0x100 + 0x30: strip kernel with a 1 KiB window (many relocation rounds) and a stream base of 6 mod 16
+@pytest.mark.parametrize("force_generic", [0, 1, 2, 0x130, 0x270])
 def test_sim_encode_default_params(sim, oracle, force_generic):
     for name, pcm in signals(oracle).items():
         for n in sorted({pcm.size, 1, 2, 19, 20, 21, 22, 41, 9999, 10000, 10001, 10019, 10020, 10021} & set(range(pcm.size + 1))):
@@ -90,6 +92,21 @@ def test_sim_encode_default_params(sim, oracle, force_generic):
             out, stats = sim_encode(sim, pcm[:n], P8(), force_generic)
             assert out.size == ref.size and np.array_equal(out, ref), (name, n)
             assert stats == rstats, (name, n)
+
+
+def test_sim_encode_strip_frame_sizes(sim, oracle):
+    """strip kernel logic with default codes / thresholds and other frame lengths (block counts that are not a multiple
+    of four, one-strip frames, the 512-block maximum), several windows and stream alignments"""
+    sig = signals(oracle)
+    for bpf in (2, 4, 6, 10, 50, 126, 498, 510, 512):
+        p8 = P8(20, bpf)
+        for name in ("s2b", "s4", "white", "clip", "small"):
+            pcm = sig[name][:min(sig[name].size, 3 * 20 * bpf + 57)]
+            ref, rstats = oracle.encode(pcm, oparams(oracle, p8))
+            for mode in (0, 0x120, 0x3e0):
+                out, stats = sim_encode(sim, pcm, p8, mode)
+                assert np.array_equal(out, ref), (bpf, name, hex(mode))
+                assert stats == rstats
 
 
 def test_sim_encode_other_params(sim, oracle):

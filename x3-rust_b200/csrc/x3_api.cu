@@ -49,6 +49,8 @@ struct DeviceState {
   uint16_t *crc_dev = nullptr;
   int sms = 0;
   bool pool_ready = false;
+  int occ[3] = {0, 0, 0};          // encode kernels: resident CTAs per SM ...
+  size_t occ_smem[3] = {0, 0, 0};  // ... at this dynamic shared-memory size
 };
 std::mutex g_dev_mu;
 DeviceState g_dev[64];
@@ -162,9 +164,20 @@ struct Derived {
   uint32_t max_blocks;
   uint32_t max_block_bits;
   uint32_t out_words_cap;
-  bool fast;
+  int kind;        // kEncKernel*: which encode kernel takes these parameters
   size_t smem;
 };
+
+// X3_ENC_KERNEL=fast selects the round-1 block-per-thread kernel instead of the strip kernel (A/B measurements)
+bool use_old_fast_kernel() {
+  static const bool v = [] { const char *e = getenv("X3_ENC_KERNEL"); return e && !strcmp(e, "fast"); }();
+  return v;
+}
+size_t encode_smem_of(int kind, const CodecParams &P, uint32_t max_blocks, uint32_t out_words_cap) {
+  return kind == kEncKernelStrip ? encode_strip_smem_bytes()
+         : kind == kEncKernelFast ? encode_fast_smem_bytes(P, out_words_cap)
+                                  : encode_smem_bytes(P, max_blocks, out_words_cap);
+}
 
 uint32_t max_block_bits_of(const x3_params *p) {
   const bool sorted = p->thresholds[0] <= p->thresholds[1] && p->thresholds[1] <= p->thresholds[2];
@@ -197,8 +210,9 @@ int derive(const x3_params *p, Derived *d) {
   d->max_block_bits = max_block_bits_of(p);
   const unsigned long long bits = 16ull + (unsigned long long)d->max_blocks * d->max_block_bits;
   d->out_words_cap = (uint32_t)((bits + 31ull) / 32ull) + 1u;
-  d->fast = params_are_default(d->P) && d->max_blocks <= 512u;
-  d->smem = d->fast ? encode_fast_smem_bytes(d->P, d->out_words_cap) : encode_smem_bytes(d->P, d->max_blocks, d->out_words_cap);
+  d->kind = kEncKernelGeneric;
+  if (params_are_default(d->P) && d->max_blocks <= 512u) d->kind = use_old_fast_kernel() ? kEncKernelFast : kEncKernelStrip;
+  d->smem = encode_smem_of(d->kind, d->P, d->max_blocks, d->out_words_cap);
   if (d->smem > kMaxDynSmem) return X3_ERR_UNSUPPORTED_PARAMS;
   return X3_OK;
 }
@@ -373,21 +387,30 @@ cudaError_t enqueue_encode(Derived d, DeviceState *ds, const int16_t *d_pcm, siz
   a.timing = reinterpret_cast<unsigned long long *>(ws + 128 + 8 * (size_t)nf);
   a.crc_tables = ds->crc_dev;
   a.neg_one = -1;
-  // the fast kernel stages frames with 16-byte cp.async: it needs a 16-byte aligned base and frame size
-  if (d.fast && ((((uintptr_t)d_pcm) & 15u) != 0 || ((d.P.spf * 2u) & 15u) != 0)) {
-    d.fast = false;
-    d.smem = encode_smem_bytes(d.P, d.max_blocks, d.out_words_cap);
+  // the fast kernels stage frames with 16-byte async copies: they need a 16-byte aligned base and frame size (and the
+  // strip kernel a 2-byte aligned output: it writes halfwords and 16-byte aligned bulk stores)
+  if (d.kind != kEncKernelGeneric && ((((uintptr_t)d_pcm) & 15u) != 0 || ((d.P.spf * 2u) & 15u) != 0 || (((uintptr_t)d_out) & 1u) != 0)) {
+    d.kind = kEncKernelGeneric;
+    d.smem = encode_smem_of(d.kind, d.P, d.max_blocks, d.out_words_cap);
     if (d.smem > kMaxDynSmem) { *rc_out = X3_ERR_UNSUPPORTED_PARAMS; return cudaSuccess; }
   }
-  const int occ = encode_occupancy(d.fast, d.smem);
+  // resident CTAs per SM of this kernel at this shared-memory size (cached: the query costs more than the launch)
+  int occ;
+  {
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    int &slot = ds->occ[d.kind];
+    size_t &slot_smem = ds->occ_smem[d.kind];
+    if (slot == 0 || slot_smem != d.smem) { slot = encode_occupancy(d.kind, d.smem); slot_smem = d.smem; }
+    occ = slot;
+  }
   unsigned long long grid = (unsigned long long)ds->sms * (unsigned)occ;
-  if (d.fast) {  // CTA 0 is the scanner, the others encode
+  if (d.kind != kEncKernelGeneric) {  // CTA 0 is the scanner, the others encode
     if (grid > nf + 1) grid = nf + 1;
     if (grid < 2) grid = 2;
   } else if (grid > nf) {
     grid = nf;
   }
-  e = launch_encode(a, d.fast, (int)grid, d.smem, st);
+  e = launch_encode(a, d.kind, (int)grid, d.smem, st);
   g_launches++;
   return e;
 }

@@ -337,7 +337,8 @@ struct FastSink {
 // thresholds, so three of them are first merged in a 32-bit register -- Horner with the powers of two 2^len as
 // multipliers, i.e. two IMADs on the FMA pipe instead of shifts and ORs on the ALU pipe -- and appended with one
 // 64-bit shift; BFP / literal samples go in pairs.
-X3_HD void block_pack_fast(const FastBlock &fb, uint32_t len, const BlockMode &m, FastSink &sink) {
+template <class Sink>
+X3_HD void block_pack_fast(const FastBlock &fb, uint32_t len, const BlockMode &m, Sink &sink) {
   const bool full = len == (uint32_t)kFastBL;
   if (m.kind == kRice) {
     sink.put(m.hdr, 2);

@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 
 #include "x3_enc_core.cuh"
+#include "x3_enc_strip.cuh"
 #include "x3_kernels.h"
 #include "x3_lookback.cuh"
 
@@ -807,6 +808,410 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const __grid
   if (tid < 6 && s_misc[40 + tid]) atomicAdd(a.result + 2 + tid, (unsigned long long)s_misc[40 + tid]);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Strip kernel: Parameters::default() and at most 512 blocks per frame (x3_enc_strip.cuh has the per-thread logic).
+//
+// 128 threads (4 warps) per CTA, one frame at a time, 5 CTAs per SM; one thread owns four consecutive blocks.  CTA 0 is
+// the scanner (scanner_role) that turns published frame sizes into stream offsets.  Per frame:
+//   stage    -- the frame's PCM lands in 176-byte rows (one per thread) by 16-byte cp.async, coalesced on the global
+//               side; it was issued while the previous frame was finishing;
+//   pack     -- every thread codes its strip in place in its own row (single pass, nothing shared);
+//   scan     -- CTA scan of the strips' bit counts; thread 0 publishes the frame size (and does NOT wait for the offset);
+//   relocate -- strips are shifted into one of TWO windows: the finished payload image;
+//   crc      -- 32-byte chunks of the window in parallel (slicing-by-4 tables in shared memory, byte-swapped state),
+//               32 chunks folded per warp by a shuffle tree, slices by Horner, tail and header CRC by one lane;
+//   out      -- the PREVIOUS frame's window goes to the stream now: its offset (which needs every earlier frame's size)
+//               has had a whole frame time to arrive.  16-byte stores, realigned with PRMT (offsets are only even).
+// A payload larger than a window (9 KiB; only literal / BFP heavy frames) is relocated, summed and written in rounds,
+// after waiting for its own offset.
+// ------------------------------------------------------------------------------------------------
+constexpr int NTS = kEncStripThreads;                 // 128
+constexpr uint32_t kWinBytes = 9216;                  // multiple of 1024 (32 chunks of 32 bytes)
+constexpr uint32_t kWinWords = kWinBytes / 4;
+constexpr uint32_t kWinSlackWords = 8;
+constexpr uint32_t kWinStride = kWinWords + kWinSlackWords;
+constexpr uint32_t kWinChunks = kWinBytes / 32;
+constexpr uint32_t kMaxSlicesStrip = 32;              // 0x7fe0 / 1024 rounded up
+constexpr uint32_t kRowsBytes = kStripMaxRows * kRowWords * 4;
+
+__device__ __forceinline__ uint32_t crc16_mulc_sw_g(const uint16_t *Tg2, int tbl, uint32_t s_sw) {
+  return (uint32_t)__ldg(Tg2 + tbl * 256 + ((s_sw >> 8) & 0xffu)) ^ (uint32_t)__ldg(Tg2 + (tbl + 1) * 256 + (s_sw & 0xffu));
+}
+
+// rows of frame f <- global, this warp's 32 rows (5120 contiguous bytes); n = samples of the frame
+__device__ __forceinline__ void stage_rows(const int16_t *frame, uint32_t n, uint32_t *s_rows, uint32_t *s_next, int wid,
+                                           int lane) {
+  const uint32_t w0 = (uint32_t)wid * 32u * kStripSamples;              // first sample of the warp's rows
+  const unsigned char *src = reinterpret_cast<const unsigned char *>(frame + w0);
+  unsigned char *dst = reinterpret_cast<unsigned char *>(s_rows + (uint32_t)wid * 32u * kRowWords);
+  const uint32_t avail = n > w0 ? n - w0 : 0u;                          // samples of the frame from w0 on
+  const uint32_t chunks = avail >> 3;                                   // whole 16-byte chunks
+#pragma unroll
+  for (uint32_t i = 0; i < 10u; i++) {
+    const uint32_t c = 32u * i + (uint32_t)lane;                        // chunk of the warp's region; row c / 10
+    if (c < chunks) cp_async16(dst + 16u * (c + ((c * 205u) >> 11)), src + 16u * c);
+  }
+  // the 81st sample of the warp's last strip: first chunk of the next warp's region
+  if (lane == 0 && chunks > 320u) cp_async16(s_next + 4 * wid, src + 5120u);
+  // samples after the last whole chunk (stream's last frame only)
+  if (avail < 32u * kStripSamples + 8u) {
+    for (uint32_t i = (chunks << 3) + (uint32_t)lane; i < avail && i < 32u * kStripSamples + 8u; i += 32u) {
+      const int16_t v = __ldg(frame + w0 + i);
+      if (i < 32u * kStripSamples) {
+        const uint32_t r = i / kStripSamples, k = i % kStripSamples;
+        reinterpret_cast<int16_t *>(s_rows + ((uint32_t)wid * 32u + r) * kRowWords)[k] = v;
+      } else {
+        reinterpret_cast<int16_t *>(s_next + 4 * wid)[i - 32u * kStripSamples] = v;
+      }
+    }
+  }
+  cp_async_commit();
+}
+
+// CRC of the whole 32-byte chunks [c_lo, c_hi) of a payload that sit in `win` from chunk c_lo on; nch = whole chunks of
+// the payload.  Slice j = the 32 chunks at distance 32j .. 32j+31 from the last whole chunk;
+// V_j ^= sum_l x^(256 l) * crc(chunk at distance 32j + l).  Called by all four warps.
+__device__ __forceinline__ void crc_slices(const uint32_t *win, uint32_t c_lo, uint32_t c_hi, uint32_t nch, uint32_t *s_V,
+                                           const uint16_t *s_T2, const uint16_t *Tg2, int wid, int lane) {
+  if (c_hi <= c_lo) return;
+  const uint32_t j_lo = (nch - c_hi) >> 5, j_hi = (nch - 1u - c_lo) >> 5;
+  for (uint32_t j = j_lo + (uint32_t)wid; j <= j_hi; j += 4u) {
+    const uint32_t e = 32u * j + (uint32_t)lane;
+    uint32_t h = 0;
+    if (e < nch) {
+      const uint32_t c = nch - 1u - e;
+      if (c >= c_lo && c < c_hi) {
+        const uint4 *q = reinterpret_cast<const uint4 *>(win) + 2u * (c - c_lo);
+        const uint4 q0 = q[0], q1 = q[1];
+        h = c == 0 ? 0xffffu : 0u;   // the CRC's initial value (byte-swapped state form)
+        h = crc16_word_sw(s_T2, h, q0.x);
+        h = crc16_word_sw(s_T2, h, q0.y);
+        h = crc16_word_sw(s_T2, h, q0.z);
+        h = crc16_word_sw(s_T2, h, q0.w);
+        h = crc16_word_sw(s_T2, h, q1.x);
+        h = crc16_word_sw(s_T2, h, q1.y);
+        h = crc16_word_sw(s_T2, h, q1.z);
+        h = crc16_word_sw(s_T2, h, q1.w);
+      }
+    }
+    h ^= crc16_mulc_sw_g(Tg2, 8, __shfl_down_sync(0xffffffffu, h, 1));     // x^256
+    h ^= crc16_mulc_sw_g(Tg2, 10, __shfl_down_sync(0xffffffffu, h, 2));    // x^512
+    h ^= crc16_mulc_sw_g(Tg2, 12, __shfl_down_sync(0xffffffffu, h, 4));    // x^1024
+    h ^= crc16_mulc_sw_g(Tg2, 14, __shfl_down_sync(0xffffffffu, h, 8));    // x^2048
+    h ^= crc16_mulc_sw_g(Tg2, 4, __shfl_down_sync(0xffffffffu, h, 16));    // x^4096
+    if (lane == 0) s_V[j] ^= h & 0xffffu;
+  }
+}
+
+// One lane: payload CRC from the slice sums (Horner, x^8192 = x^4096 twice) and the bytes after the last whole chunk,
+// which lie in `win` at byte `tail_at`; returns (header CRC << 16) | payload CRC for the frame header.
+__device__ __forceinline__ uint32_t crc_finish(const uint32_t *s_V, const uint32_t *win, uint32_t tail_at, uint32_t payload_len,
+                                               uint32_t n, const uint16_t *s_T2, const uint16_t *Tg2) {
+  const uint32_t nch = payload_len >> 5, nsl = (nch + 31u) >> 5;
+  uint32_t s = 0;
+  for (int j = (int)nsl - 1; j >= 0; j--) s = crc16_mulc_sw_g(Tg2, 4, crc16_mulc_sw_g(Tg2, 4, s)) ^ s_V[j];
+  if (nch == 0) s = 0xffffu;
+  uint32_t rem = payload_len & 31u, wi = tail_at >> 2;   // rem is even
+  for (; rem >= 4u; rem -= 4u) s = crc16_word_sw(s_T2, s, win[wi++]);
+  if (rem) s = crc16_half_sw(s_T2, s, win[wi] & 0xffffu);
+  return (header_crc_sw(s_T2, 1u, n, payload_len) << 16) | bswap16(s);
+}
+
+// payload image (16-byte aligned in shared memory) -> dst (2-byte aligned global address), all NTS threads.
+// Body in 16-byte stores; the shared-memory side is read at a 2- or 4-byte skew and realigned with PRMT.
+__device__ __forceinline__ void copy_window_out(unsigned char *dst, const uint32_t *s_words, uint32_t L, int tid) {
+  uint32_t head = (uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u);  // bytes until dst is 16-byte aligned (even)
+  if (head > L) head = L;
+  const uint32_t nvec = (L - head) >> 4;
+  const uint32_t tail0 = head + (nvec << 4);
+  const uint16_t *s16 = reinterpret_cast<const uint16_t *>(s_words);
+  if ((uint32_t)tid < (head >> 1)) reinterpret_cast<uint16_t *>(dst)[tid] = s16[tid];
+  if ((uint32_t)tid >= 32u && (uint32_t)tid - 32u < ((L - tail0) >> 1))
+    reinterpret_cast<uint16_t *>(dst + tail0)[tid - 32] = s16[(tail0 >> 1) + (tid - 32)];
+  uint4 *d4 = reinterpret_cast<uint4 *>(dst + head);
+  const uint32_t w0 = head >> 2;          // first source word
+  if ((head & 3u) == 0u) {
+    for (uint32_t i = tid; i < nvec; i += NTS) {
+      const uint32_t *q = s_words + w0 + 4u * i;
+      uint4 v;
+      v.x = q[0]; v.y = q[1]; v.z = q[2]; v.w = q[3];
+      d4[i] = v;
+    }
+  } else {                                // source starts in the middle of a word
+    for (uint32_t i = tid; i < nvec; i += NTS) {
+      const uint32_t *q = s_words + w0 + 4u * i;
+      const uint32_t a0 = q[0], a1 = q[1], a2 = q[2], a3 = q[3], a4 = q[4];
+      uint4 v;
+      v.x = __byte_perm(a0, a1, 0x5432); v.y = __byte_perm(a1, a2, 0x5432);
+      v.z = __byte_perm(a2, a3, 0x5432); v.w = __byte_perm(a3, a4, 0x5432);
+      d4[i] = v;
+    }
+  }
+}
+
+// header of a frame at out + goff: ten big-endian halfwords written by lanes 0..9 of one warp
+// (id = 1 for audio frames, encoder.rs:210; time = 0, :148-150)
+__device__ __forceinline__ void write_header(unsigned char *out, unsigned long long goff, uint32_t n, uint32_t payload_len,
+                                             uint32_t hw, int lane) {
+  if (lane < 10) {
+    uint32_t v = 0;
+    if (lane == 0) v = kFrameKey;
+    else if (lane == 1) v = 0x0101u;
+    else if (lane == 2) v = n & 0xffffu;
+    else if (lane == 3) v = payload_len & 0xffffu;
+    else if (lane == 8) v = hw >> 16;
+    else if (lane == 9) v = hw & 0xffffu;
+    reinterpret_cast<uint16_t *>(out + goff)[lane] = (uint16_t)(((v & 0xff) << 8) | (v >> 8));
+  }
+}
+
+// stream offset of frame f: wait for the scanner to turn the published size into a prefix (one thread)
+__device__ __forceinline__ unsigned long long wait_offset(const EncodeArgs &a, uint32_t f, uint32_t frame_bytes, bool &fits) {
+  unsigned long long pv;
+  while (((pv = ld_status(a.status + f)) >> 62) != 2ull) __nanosleep(32);
+  const unsigned long long excl = (pv & kValueMask) - frame_bytes;
+  fits = excl + frame_bytes <= a.out_cap;
+  if (!fits) atomicMax(a.result + 1, 1ull);            // ByteWriterInsufficientMemory, bytewriter.rs:88
+  return excl;
+}
+
+__global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __grid_constant__ EncodeArgs a) {
+  if (blockIdx.x == 0) {
+    scanner_role(a);
+    return;
+  }
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t *s_rows = reinterpret_cast<uint32_t *>(smem_raw);
+  uint32_t *s_win = reinterpret_cast<uint32_t *>(smem_raw + kRowsBytes);                      // 2 windows
+  uint16_t *s_T2 = reinterpret_cast<uint16_t *>(s_win + 2u * kWinStride);
+  uint32_t *s_next = reinterpret_cast<uint32_t *>(s_T2 + 1024);                               // 4 x 16 bytes
+  uint32_t *s_V = s_next + 16;                                                                // kMaxSlicesStrip
+  uint32_t *s_misc = s_V + kMaxSlicesStrip;
+  // s_misc: [0..4) warp totals, [8] this CTA's next frame, [10],[11] stream offset, [12] fits, [16..22) stats,
+  //         per window q at [24 + 4q ..): +0 frame (kNoFrame: nothing pending), +1 samples, +2 payload_len, +3 header CRC | payload CRC
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint16_t *Tg2 = a.crc_tables + kCrcTableEntries;     // byte-swapped bank (global): tree / Horner constants
+  for (int i = tid; i < 1024; i += NTS) s_T2[i] = Tg2[i];
+  if (tid < 6) s_misc[16 + tid] = 0;
+  if (tid == 0) {
+    s_misc[8] = atomicAdd(a.ticket, 1u);
+    s_misc[24] = kNoFrame;
+    s_misc[28] = kNoFrame;
+  }
+  __syncthreads();
+  const uint32_t spf = a.P.spf;
+  const uint32_t last_f = a.n_frames - 1u;
+  const uint32_t last_n = (uint32_t)(a.n_samples - (unsigned long long)last_f * spf);
+  uint32_t f = s_misc[8];
+  if (f < a.n_frames) stage_rows(a.pcm + (unsigned long long)f * spf, f == last_f ? last_n : spf, s_rows, s_next, wid, lane);
+  unsigned long long stat_acc = 0;
+  uint32_t it = 0, par = 0;
+  uint32_t *row = s_rows + (uint32_t)tid * kRowWords;
+
+  while (f < a.n_frames) {
+    const uint32_t n = f == last_f ? last_n : spf;
+    const uint32_t nblk = n > 1 ? (n - 2u) / 20u + 1u : 1u;
+    cp_async_wait_all();
+    __syncthreads();                                   // (B0) rows staged; the previous copy-out is complete
+
+    // ---- local pack ----
+    uint32_t T = 0;
+    {
+      const uint32_t nxt = lane == 31 ? s_next[4 * wid] : row[kRowWords];
+      __syncwarp();                                    // every lane has its look-ahead word before any row changes
+      const uint32_t b0 = kStripBlocks * (uint32_t)tid;
+      if (b0 < nblk) {
+        if (b0 + kStripBlocks <= nblk && n >= kStripSamples * ((uint32_t)tid + 1u)) {
+          const bool full = n > kStripSamples * ((uint32_t)tid + 1u);
+          uint32_t s19 = 0;
+          T = strip_pack_fast(row, nxt, full, tid == 0, a.neg_one, stat_acc, s19);
+          if (!full) atomicAdd(&s_misc[16 + s19], 19u);
+        } else {
+          uint32_t ss[6] = {0, 0, 0, 0, 0, 0};
+          T = strip_pack_generic(row, nxt, (uint32_t)tid, n, nblk, a.P, ss);
+#pragma unroll
+          for (int m = 0; m < 6; m++)
+            if (ss[m]) atomicAdd(&s_misc[16 + m], ss[m]);
+        }
+      }
+    }
+
+    // ---- CTA scan of the strips' bit counts ----
+    uint32_t incl = T;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_misc[wid] = incl;
+    if (tid >= 32 && tid < 32 + (int)kMaxSlicesStrip) s_V[tid - 32] = 0u;
+    __syncthreads();                                   // (B1)
+    const uint32_t w0 = s_misc[0], w1 = s_misc[1], w2 = s_misc[2], w3 = s_misc[3];
+    const uint32_t total_bits = w0 + w1 + w2 + w3;
+    const uint32_t wbase = (wid > 0 ? w0 : 0u) + (wid > 1 ? w1 : 0u) + (wid > 2 ? w2 : 0u);
+    const uint32_t O = wbase + incl - T;
+    const uint32_t payload_len = payload_bytes(total_bits);
+    const uint32_t frame_bytes = (uint32_t)kFrameHeaderLen + payload_len;
+    const uint32_t nch = payload_len >> 5;             // whole 32-byte CRC chunks
+    uint32_t *win = s_win + par * kWinStride;
+    const uint32_t prev = par ^ 1u;
+    if (tid == 0) {
+      st_status(a.status + f, kFlagAgg | (unsigned long long)frame_bytes);   // publish the size; nobody waits here
+      s_misc[8] = atomicAdd(a.ticket, 1u);
+    }
+
+    if (payload_len <= kWinBytes) {
+      // ================= the frame fits a window: relocate, sum, and let the PREVIOUS frame go out =================
+      if (tid == 0) {
+        win[total_bits >> 5] = 0u;                     // completed by nobody: tails OR into it
+        win[(total_bits >> 5) + 1] = 0u;               // padding to an even byte count
+      }
+      uint32_t tail;
+      int32_t tail_idx;
+      strip_relocate(row, T, (int32_t)O, win, kWinWords, tail, tail_idx);
+      __syncthreads();                                 // (B3) plain stores done; rows are free
+      if (tail_idx >= 0) atomicOr(&win[tail_idx], tail);
+      const uint32_t f_next = s_misc[8];
+      if (f_next < a.n_frames)
+        stage_rows(a.pcm + (unsigned long long)f_next * spf, f_next == last_f ? last_n : spf, s_rows, s_next, wid, lane);
+      __syncthreads();                                 // (B4) window complete
+      // offset of the previous frame (published a frame time ago): one thread asks while the others sum this frame
+      uint32_t *pinfo = s_misc + 24 + 4 * prev;
+      const uint32_t pf = pinfo[0];
+      if (tid == 32 && pf != kNoFrame) {
+        bool fits;
+        const unsigned long long excl = wait_offset(a, pf, (uint32_t)kFrameHeaderLen + pinfo[2], fits);
+        s_misc[10] = (uint32_t)excl;
+        s_misc[11] = (uint32_t)(excl >> 32);
+        s_misc[12] = fits ? 1u : 0u;
+      }
+      crc_slices(win, 0u, nch, nch, s_V, s_T2, Tg2, wid, lane);
+      __syncthreads();                                 // (B5) slice CRCs and the previous frame's offset are there
+      if (wid == 0) {
+        uint32_t hw = 0;
+        if (lane == 0) {
+          hw = crc_finish(s_V, win, 32u * nch, payload_len, n, s_T2, Tg2);
+          uint32_t *info = s_misc + 24 + 4 * par;
+          info[0] = f; info[1] = n; info[2] = payload_len; info[3] = hw;
+        }
+      }
+      if (pf != kNoFrame) {
+        if (s_misc[12]) {
+          const unsigned long long goff = (unsigned long long)s_misc[10] | ((unsigned long long)s_misc[11] << 32);
+          copy_window_out(a.out + goff + kFrameHeaderLen, s_win + prev * kWinStride, pinfo[2], tid);
+          if (wid == 1) write_header(a.out, goff, pinfo[1], pinfo[2], pinfo[3], lane);
+        }
+      }
+      // pinfo[0] is overwritten with this slot's next frame two iterations from now (or cleared by the big-frame path)
+      f = f_next;
+      par ^= 1u;
+    } else {
+      // ================= big frame: rounds through window `par`, written out as they come =================
+      __syncthreads();                                 // (C0) ticket visible
+      const uint32_t f_next = s_misc[8];
+      // the pending frame first (stream order is not required, but its window slot and info are reused below)
+      uint32_t *pinfo = s_misc + 24 + 4 * prev;
+      const uint32_t pf = pinfo[0];
+      if (tid == 32) {
+        bool fits;
+        if (pf != kNoFrame) {
+          const unsigned long long excl = wait_offset(a, pf, (uint32_t)kFrameHeaderLen + pinfo[2], fits);
+          s_misc[10] = (uint32_t)excl;
+          s_misc[11] = (uint32_t)(excl >> 32);
+          s_misc[12] = fits ? 1u : 0u;
+        }
+        const unsigned long long excl2 = wait_offset(a, f, frame_bytes, fits);
+        s_misc[13] = (uint32_t)excl2;
+        s_misc[14] = (uint32_t)(excl2 >> 32);
+        s_misc[15] = fits ? 1u : 0u;
+      }
+      __syncthreads();                                 // (C1)
+      if (pf != kNoFrame && s_misc[12]) {
+        const unsigned long long goff = (unsigned long long)s_misc[10] | ((unsigned long long)s_misc[11] << 32);
+        copy_window_out(a.out + goff + kFrameHeaderLen, s_win + prev * kWinStride, pinfo[2], tid);
+        if (wid == 1) write_header(a.out, goff, pinfo[1], pinfo[2], pinfo[3], lane);
+      }
+      const unsigned long long goff = (unsigned long long)s_misc[13] | ((unsigned long long)s_misc[14] << 32);
+      const bool fits = s_misc[15] != 0u;
+      const uint32_t nrounds = (payload_len + kWinBytes - 1u) / kWinBytes;
+      for (uint32_t r = 0; r < nrounds; r++) {
+        const int32_t wbit0 = (int32_t)(8u * r * kWinBytes);
+        if (tid == 0) {
+          const int32_t zt = (int32_t)total_bits - wbit0;
+          if (zt >= 0 && (zt >> 5) < (int32_t)kWinWords) {
+            win[zt >> 5] = 0u;
+            win[(zt >> 5) + 1] = 0u;
+          }
+        }
+        uint32_t tail;
+        int32_t tail_idx;
+        strip_relocate(row, T, (int32_t)O - wbit0, win, kWinWords, tail, tail_idx);
+        __syncthreads();
+        if (tail_idx >= 0) atomicOr(&win[tail_idx], tail);
+        if (r == nrounds - 1u && f_next < a.n_frames)
+          stage_rows(a.pcm + (unsigned long long)f_next * spf, f_next == last_f ? last_n : spf, s_rows, s_next, wid, lane);
+        __syncthreads();
+        const uint32_t vb1 = payload_len - r * kWinBytes < kWinBytes ? payload_len - r * kWinBytes : kWinBytes;
+        const uint32_t c_lo = r * kWinChunks, c_hi = nch < (r + 1u) * kWinChunks ? nch : (r + 1u) * kWinChunks;
+        crc_slices(win, c_lo, c_hi, nch, s_V, s_T2, Tg2, wid, lane);
+        if (fits) copy_window_out(a.out + goff + kFrameHeaderLen + (size_t)r * kWinBytes, win, vb1, tid);
+        __syncthreads();                               // window reused by the next round; slice sums complete
+      }
+      if (wid == 0) {
+        uint32_t hw = 0;
+        if (lane == 0) hw = crc_finish(s_V, win, 32u * nch - (nrounds - 1u) * kWinBytes, payload_len, n, s_T2, Tg2);
+        hw = __shfl_sync(0xffffffffu, hw, 0);
+        if (fits) write_header(a.out, goff, n, payload_len, hw, lane);
+        if (lane == 0) {
+          s_misc[24] = kNoFrame;                       // nothing pending in either window
+          s_misc[28] = kNoFrame;
+        }
+      }
+      f = f_next;
+    }
+    it++;
+    if ((it & 127u) == 0u) {                           // the 10-bit counters (4 blocks per frame) are about to fill up
+#pragma unroll
+      for (int m = 0; m < 6; m++) {
+        const uint32_t c = (uint32_t)(stat_acc >> (10 * m)) & 1023u;
+        if (c) atomicAdd(&s_misc[16 + m], c * 20u);
+      }
+      stat_acc = 0;
+    }
+  }
+  // ---- drain: the last frame of this CTA is still in its window ----
+  __syncthreads();
+  {
+    const uint32_t prev = par ^ 1u;
+    uint32_t *pinfo = s_misc + 24 + 4 * prev;
+    const uint32_t pf = pinfo[0];
+    if (pf != kNoFrame) {
+      if (tid == 32) {
+        bool fits;
+        const unsigned long long excl = wait_offset(a, pf, (uint32_t)kFrameHeaderLen + pinfo[2], fits);
+        s_misc[10] = (uint32_t)excl;
+        s_misc[11] = (uint32_t)(excl >> 32);
+        s_misc[12] = fits ? 1u : 0u;
+      }
+      __syncthreads();
+      if (s_misc[12]) {
+        const unsigned long long goff = (unsigned long long)s_misc[10] | ((unsigned long long)s_misc[11] << 32);
+        copy_window_out(a.out + goff + kFrameHeaderLen, s_win + prev * kWinStride, pinfo[2], tid);
+        if (wid == 1) write_header(a.out, goff, pinfo[1], pinfo[2], pinfo[3], lane);
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < 6; m++) {
+    const uint32_t c = (uint32_t)(stat_acc >> (10 * m)) & 1023u;
+    if (c) atomicAdd(&s_misc[16 + m], c * 20u);
+  }
+  __syncthreads();
+  if (tid < 6 && s_misc[16 + tid]) atomicAdd(a.result + 2 + tid, (unsigned long long)s_misc[16 + tid]);
+}
+
 }  // namespace
 
 size_t encode_smem_bytes(const CodecParams &P, uint32_t max_blocks, uint32_t out_words_cap) {
@@ -824,9 +1229,17 @@ size_t encode_fast_smem_bytes(const CodecParams &P, uint32_t out_words_cap) {
   return (size_t)in_bytes + NB * img_bytes + kCrcBankEntries2 * 2 + NB * kMaxSlices * 4u + 96u * 4u;
 }
 
-cudaError_t launch_encode(const EncodeArgs &a, bool fast, int grid, size_t smem, cudaStream_t stream) {
+size_t encode_strip_smem_bytes() {
+  return (size_t)kRowsBytes + 2u * kWinStride * 4u + 1024u * 2u + 16u * 4u + kMaxSlicesStrip * 4u + 40u * 4u;
+}
+
+cudaError_t launch_encode(const EncodeArgs &a, int kind, int grid, size_t smem, cudaStream_t stream) {
   cudaError_t e;
-  if (fast) {
+  if (kind == kEncKernelStrip) {
+    e = cudaFuncSetAttribute(encode_frames_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    encode_frames_strip_kernel<<<grid, NTS, smem, stream>>>(a);
+  } else if (kind == kEncKernelFast) {
     const bool std_frame = a.P.spf == kStdSpf && a.out_words_cap == kStdOwc;
     auto kern = std_frame ? encode_frames_fast_kernel<kStdSpf, kStdOwc> : encode_frames_fast_kernel<0, 0>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -840,10 +1253,13 @@ cudaError_t launch_encode(const EncodeArgs &a, bool fast, int grid, size_t smem,
   return cudaGetLastError();
 }
 
-int encode_occupancy(bool fast, size_t smem) {
+int encode_occupancy(int kind, size_t smem) {
   int nb = 0;
   cudaError_t e;
-  if (fast) {
+  if (kind == kEncKernelStrip) {
+    cudaFuncSetAttribute(encode_frames_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, encode_frames_strip_kernel, NTS, smem);
+  } else if (kind == kEncKernelFast) {
     cudaFuncSetAttribute(encode_frames_fast_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, encode_frames_fast_kernel<0, 0>, NTF, smem);
   } else {

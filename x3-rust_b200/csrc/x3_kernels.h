@@ -11,6 +11,8 @@ namespace x3 {
 
 constexpr int kEncThreads = 512;       // generic kernel
 constexpr int kEncFastThreads = 544;   // fast kernel: 16 worker warps + 1 control warp
+constexpr int kEncStripThreads = 128;  // strip kernel: 4 warps, one thread per four blocks
+enum : int { kEncKernelGeneric = 0, kEncKernelFast = 1, kEncKernelStrip = 2 };
 #ifndef X3_DEC_THREADS
 #define X3_DEC_THREADS 128
 #endif
@@ -39,8 +41,9 @@ struct EncodeArgs {
 
 size_t encode_smem_bytes(const CodecParams &P, uint32_t max_blocks, uint32_t out_words_cap);
 size_t encode_fast_smem_bytes(const CodecParams &P, uint32_t out_words_cap);
-int encode_occupancy(bool fast, size_t smem);
-cudaError_t launch_encode(const EncodeArgs &a, bool fast, int grid, size_t smem, cudaStream_t stream);
+size_t encode_strip_smem_bytes();
+int encode_occupancy(int kind, size_t smem);
+cudaError_t launch_encode(const EncodeArgs &a, int kind, int grid, size_t smem, cudaStream_t stream);
 
 // One frame of a stream, as found by the frame index (device scan or host walk).
 struct FrameRec {

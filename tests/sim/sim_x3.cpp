@@ -168,7 +168,7 @@ size_t sim_encode_frame_strip(const int16_t *pcm, uint32_t n, const CodecParams 
   for (uint32_t w = 0; w < 4; w++) {
     const uint32_t w0 = w * 32u * kStripSamples;
     const uint32_t avail = n > w0 ? n - w0 : 0u, chunks = avail >> 3;
-    unsigned char *dst = reinterpret_cast<unsigned char *>(rows.data() + w * 32u * kRowWords);
+    unsigned char *dst = reinterpret_cast<unsigned char *>(rows.data() + w * 32u * kRowWords + kRowPadWords);
     for (uint32_t c = 0; c < 320u && c < chunks; c++) {
       if (((c * 205u) >> 11) != c / 10u) return 0;
       memcpy(dst + 16u * (c + ((c * 205u) >> 11)), pcm + w0 + 8u * c, 16);
@@ -177,13 +177,13 @@ size_t sim_encode_frame_strip(const int16_t *pcm, uint32_t n, const CodecParams 
     if (avail < 32u * kStripSamples + 8u)
       for (uint32_t i = chunks << 3; i < avail && i < 32u * kStripSamples + 8u; i++) {
         if (i < 32u * kStripSamples)
-          reinterpret_cast<int16_t *>(rows.data() + (w * 32u + i / kStripSamples) * kRowWords)[i % kStripSamples] = pcm[w0 + i];
+          reinterpret_cast<int16_t *>(rows.data() + (w * 32u + i / kStripSamples) * kRowWords + kRowPadWords)[i % kStripSamples] = pcm[w0 + i];
         else
           reinterpret_cast<int16_t *>(s_next[w])[i - 32u * kStripSamples] = pcm[w0 + i];
       }
   }
   uint32_t nxt[128], Tb[128], O[128];
-  for (uint32_t t = 0; t < 128; t++) nxt[t] = (t & 31u) == 31u ? s_next[t >> 5][0] : rows[(t + 1) * kRowWords];
+  for (uint32_t t = 0; t < 128; t++) nxt[t] = (t & 31u) == 31u ? s_next[t >> 5][0] : rows[(t + 1) * kRowWords + kRowPadWords];
   uint32_t short_stats[6] = {0, 0, 0, 0, 0, 0};
   unsigned long long stat_acc_sum[6] = {0, 0, 0, 0, 0, 0};
   for (uint32_t t = 0; t < 128; t++) {
@@ -211,6 +211,11 @@ size_t sim_encode_frame_strip(const int16_t *pcm, uint32_t n, const CodecParams 
   const uint32_t nrounds = (end_bytes + win_bytes - 1u) / win_bytes, nch = end_bytes >> 5;
   std::vector<uint32_t> win(win_words + 8u);
   std::vector<uint32_t> V(64, 0u);
+  // regular frames (the kernel's common path): every strip but the last has >= 32 bits, the payload fits the window,
+  // the window is 16-byte aligned to the payload: relocation without merging (strip_relocate_fast)
+  const uint32_t nstrips = (nblk + kStripBlocks - 1u) / kStripBlocks;
+  bool regular = payload_len <= win_bytes && a_off == 0u;
+  for (uint32_t t = 0; t + 1u < nstrips; t++) regular = regular && Tb[t] >= 32u;
   std::vector<uint8_t> image(end_bytes + 64u, 0xEE);   // window-space bytes as written to the stream
   for (uint32_t r = 0; r < nrounds; r++) {
     std::fill(win.begin(), win.end(), 0xdeadbeefu);     // stale data of the previous round / frame
@@ -218,12 +223,18 @@ size_t sim_encode_frame_strip(const int16_t *pcm, uint32_t n, const CodecParams 
     if (r == 0) for (uint32_t k = 0; k < (a_off >> 2); k++) win[k] = 0u;
     const int32_t zt = (int32_t)(8u * a_off + total_bits) - wbit0;
     if (zt >= 0 && (zt >> 5) < (int32_t)win_words) { win[zt >> 5] = 0u; win[(zt >> 5) + 1] = 0u; }
-    uint32_t tail[128];
-    int32_t tail_idx[128];
-    for (uint32_t t = 0; t < 128; t++)
-      strip_relocate(rows.data() + t * kRowWords, Tb[t], (int32_t)(8u * a_off + O[t]) - wbit0, win.data(), win_words, tail[t], tail_idx[t]);
-    for (uint32_t t = 0; t < 128; t++)
-      if (tail_idx[t] >= 0) win[tail_idx[t]] |= tail[t];
+    if (regular) {
+      std::fill(win.begin(), win.end(), 0xdeadbeefu);
+      for (uint32_t t = 0; t < nstrips; t++)
+        strip_relocate_fast(rows.data() + t * kRowWords, Tb[t], O[t], t ? Tb[t - 1] : 32u, t + 1u == nstrips, win.data());
+    } else {
+      uint32_t tail[128];
+      int32_t tail_idx[128];
+      for (uint32_t t = 0; t < 128; t++)
+        strip_relocate(rows.data() + t * kRowWords, Tb[t], (int32_t)(8u * a_off + O[t]) - wbit0, win.data(), win_words, tail[t], tail_idx[t]);
+      for (uint32_t t = 0; t < 128; t++)
+        if (tail_idx[t] >= 0) win[tail_idx[t]] |= tail[t];
+    }
     const uint32_t vb0 = r == 0 ? a_off : 0u;
     const uint32_t vb1 = end_bytes - r * win_bytes < win_bytes ? end_bytes - r * win_bytes : win_bytes;
     memcpy(image.data() + r * win_bytes + vb0, reinterpret_cast<const uint8_t *>(win.data()) + vb0, vb1 - vb0);

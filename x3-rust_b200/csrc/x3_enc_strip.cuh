@@ -5,9 +5,11 @@
 // once per four blocks.  The frame is encoded in ONE pass over the samples:
 //   1. local pack  -- the thread codes its blocks (encoder.rs:289-315, same per-block functions as the other
 //                     kernels) into a bit string that starts at bit 0 of ITS OWN ROW of the staging buffer, in place:
-//                     the row (176 bytes) first holds the strip's 160 bytes of PCM, then its code bits (at most
-//                     16 + 4*326 bits = 168 bytes).  No other thread touches the row, so there is nothing to merge
-//                     and nothing to wait for; the bit count T of the strip falls out of the packing.
+//                     the row (176 bytes = 16 bytes of padding + the strip's 160 bytes of PCM) ends up holding the
+//                     strip's code bits (at most 16 + 4*326 bits = 168 bytes).  The bit string starts in the padding
+//                     and grows more slowly than the samples are consumed (a block of 40 bytes codes to at most 41),
+//                     so it never reaches a block that has not been loaded yet.  No other thread touches the row, so
+//                     there is nothing to merge and nothing to wait for; the bit count T falls out of the packing.
 //   2. scan        -- CTA exclusive scan of T -> the strip's bit offset O in the frame payload; frame size published.
 //   3. relocate    -- the thread shifts its local words by (O + 8*a) mod 32 into the frame image ("window"), where a
 //                     is the payload's global byte address mod 16: the image is then byte-for-byte what the stream
@@ -23,6 +25,7 @@ namespace x3 {
 constexpr uint32_t kStripBlocks = 4;
 constexpr uint32_t kStripSamples = kStripBlocks * (uint32_t)kFastBL;  // 80
 constexpr uint32_t kRowWords = 44;        // 176-byte rows: 16-byte vector loads of 32 consecutive rows hit 32 distinct bank groups
+constexpr uint32_t kRowPadWords = 4;      // the strip's samples start 16 bytes into the row
 constexpr uint32_t kStripMaxRows = 128;   // <= 512 blocks per frame
 
 // MSB-first bit sink into the thread's own row (big-endian valued words, no byte swap).  Same contract as FastSink:
@@ -54,11 +57,13 @@ struct RowSink {
 #endif
     cnt &= 31u;
   }
-  // end of the strip: the last partial word goes out zero padded; returns the strip's bit count
+  // end of the strip: the last partial word goes out zero padded, and one zero word after the bit string (the
+  // relocation reads one word past the end); returns the strip's bit count
   X3_HD uint32_t finish(uint32_t *row) {
     flush();
     const uint32_t w = cnt ? (uint32_t)(acc << (32u - cnt)) : 0u;
-    sm_store_if(cnt != 0u, dst, w);
+    sm_store_if(true, dst, w);
+    sm_store_if(cnt != 0u, sm_advance(dst, 1), 0u);
 #if defined(__CUDA_ARCH__)
     return 8u * (dst - sm_addr(row)) + cnt;
 #else
@@ -67,25 +72,22 @@ struct RowSink {
   }
 };
 
-// the eleven words (s[20b], s[20b+1]) ... (s[20b+20], s[20b+21]) of block j of the strip; word 10 of the last block
-// is the first word of the next strip's row, read ahead of time by the caller (`nxt`)
-template <int J>
-X3_HD void strip_load_words(const uint32_t *row, uint32_t nxt, uint32_t W[kFastBL / 2 + 1]) {
-  const uint32_t *p = row + 10 * J;
+// the eleven words (s[20b], s[20b+1]) ... (s[20b+20], s[20b+21]) of block j of the strip (8-byte aligned in the row);
+// word 10 of the last block is the first word of the next strip's samples, read ahead of time by the caller (`nxt`)
+X3_HD void strip_load_words(const uint32_t *row, uint32_t j, uint32_t nxt, uint32_t W[kFastBL / 2 + 1]) {
+  const uint32_t *p = row + kRowPadWords + 10u * j;
 #if defined(__CUDA_ARCH__)
-  if ((J & 1) == 0) {  // byte offset 40*J is a multiple of 16
-    const uint4 a = *reinterpret_cast<const uint4 *>(p), b = *reinterpret_cast<const uint4 *>(p + 4);
-    const uint2 c = *reinterpret_cast<const uint2 *>(p + 8);
-    W[0] = a.x; W[1] = a.y; W[2] = a.z; W[3] = a.w; W[4] = b.x; W[5] = b.y; W[6] = b.z; W[7] = b.w; W[8] = c.x; W[9] = c.y;
-  } else {             // 8 mod 16
-    const uint2 a = *reinterpret_cast<const uint2 *>(p);
-    const uint4 b = *reinterpret_cast<const uint4 *>(p + 2), c = *reinterpret_cast<const uint4 *>(p + 6);
-    W[0] = a.x; W[1] = a.y; W[2] = b.x; W[3] = b.y; W[4] = b.z; W[5] = b.w; W[6] = c.x; W[7] = c.y; W[8] = c.z; W[9] = c.w;
+  const uint2 *p2 = reinterpret_cast<const uint2 *>(p);
+#pragma unroll
+  for (int i = 0; i < 5; i++) {
+    const uint2 v = p2[i];
+    W[2 * i] = v.x;
+    W[2 * i + 1] = v.y;
   }
 #else
   for (int i = 0; i < 10; i++) W[i] = p[i];
 #endif
-  W[10] = J == (int)kStripBlocks - 1 ? nxt : p[10];
+  W[10] = j == kStripBlocks - 1u ? nxt : p[10];
 }
 
 // Folded differences and mode of one block of 20 (full) or 19 samples from its eleven words: block_measure_fast
@@ -126,32 +128,29 @@ X3_HD BlockMode block_fold_fast(const uint32_t W[kFastBL / 2 + 1], bool full, Fa
 // Local pack of a strip whose four blocks are all there: 20, 20, 20 and 20 (`full`) or 19 samples.
 // `first`: the strip starts the frame, its bit string begins with the <Audio State> (encoder.rs:189).
 // stat_acc: six 10-bit counters of full blocks per mode; len19_stat: stats index of the 19-sample block, if any.
-// The words of block j+1 are loaded before block j is packed: the bit string grows over the samples it replaces
-// (a block of 40 bytes can code to 41), but never over a block that has not been loaded yet.
+// One copy of the block coder, four trips (the unrolled form is 58 KB of code: the kernel then waits for instructions).
 X3_HD uint32_t strip_pack_fast(uint32_t *row, uint32_t nxt, bool full, bool first, int32_t neg1,
                                unsigned long long &stat_acc, uint32_t &len19_stat) {
-  uint32_t Wa[kFastBL / 2 + 1], Wb[kFastBL / 2 + 1];
-  FastBlock fb;
   RowSink sink;
   sink.init(row);
-  strip_load_words<0>(row, nxt, Wa);
   if (first) {
-    sink.put(Wa[0] & 0xffffu, 16);
+    sink.put(row[kRowPadWords] & 0xffffu, 16);
     sink.flush();
   }
-  BlockMode m;
-#define X3_STRIP_BLOCK(J, WCUR, WNEXT, FULL)                          \
-  if (J + 1 < (int)kStripBlocks) strip_load_words<(J + 1) & 3>(row, nxt, WNEXT); \
-  m = block_fold_fast(WCUR, FULL, fb, neg1);                          \
-  if (FULL) stat_acc += 1ull << (10u * m.stat);                       \
-  else len19_stat = m.stat;                                           \
-  block_pack_fast(fb, (FULL) ? 20u : 19u, m, sink);                   \
-  sink.flush();
-  X3_STRIP_BLOCK(0, Wa, Wb, true)
-  X3_STRIP_BLOCK(1, Wb, Wa, true)
-  X3_STRIP_BLOCK(2, Wa, Wb, true)
-  X3_STRIP_BLOCK(3, Wb, Wa, full)
-#undef X3_STRIP_BLOCK
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (uint32_t j = 0; j < kStripBlocks; j++) {
+    uint32_t W[kFastBL / 2 + 1];
+    FastBlock fb;
+    strip_load_words(row, j, nxt, W);
+    const bool fullj = full || j != kStripBlocks - 1u;
+    const BlockMode m = block_fold_fast(W, fullj, fb, neg1);
+    if (fullj) stat_acc += 1ull << (10u * m.stat);
+    else len19_stat = m.stat;
+    block_pack_fast(fb, fullj ? 20u : 19u, m, sink);
+    sink.flush();
+  }
   return sink.finish(row);
 }
 
@@ -162,7 +161,7 @@ X3_HD uint32_t strip_pack_generic(uint32_t *row, uint32_t nxt, uint32_t strip, u
                                   const CodecParams &P, uint32_t short_stats[6]) {
   int16_t loc[kStripSamples + 2];
   for (uint32_t i = 0; i < kStripSamples / 2; i++) {
-    const uint32_t w = row[i];
+    const uint32_t w = row[kRowPadWords + i];
     loc[2 * i] = (int16_t)(w & 0xffffu);
     loc[2 * i + 1] = (int16_t)(w >> 16);
   }
@@ -216,6 +215,51 @@ X3_HD void strip_relocate(const uint32_t *row, uint32_t T, int32_t start, uint32
       tail_idx = d;
     }
   }
+}
+
+// Step 3, regular frames (every strip but the last holds at least 32 bits, the payload fits the window): no merging.
+// A window word holds bits of at most two strips; it is stored by the strip that holds its last bit, which fetches the
+// other strip's bits -- the last (start & 31) bits of its predecessor -- from the predecessor's row itself.  The last
+// strip of the frame also stores its final partial word (the window is 16-bit aligned, so the padding to an even
+// byte count never leaves that word).
+// start = bit offset of the strip in the window, Tp = bit count of the predecessor (row - kRowWords).
+X3_HD void strip_relocate_fast(const uint32_t *row, uint32_t T, uint32_t start, uint32_t Tp, bool last, uint32_t *win) {
+  const uint32_t s = start & 31u;
+  uint32_t *dst = win + (start >> 5);
+  uint32_t nst = (s + T) >> 5;                       // words whose last bit is this strip's
+  if (last && ((s + T) & 31u)) nst += 1u;            // + the final partial word (its zero bits are the even-byte padding)
+  uint32_t pred = 0;
+  if (s) {                                           // the predecessor's last s bits, left aligned
+    const uint32_t *prow = row - kRowWords;
+    const uint32_t e = Tp - s;                       // Tp >= 32 > s
+    pred = funnel_l(prow[(e >> 5) + 1u], prow[e >> 5], e & 31u) & ~(0xffffffffu >> s);
+  }
+  uint32_t prevw = 0;
+#if defined(__CUDA_ARCH__)
+  const uint4 *row4 = reinterpret_cast<const uint4 *>(row);
+#pragma unroll 1
+  for (uint32_t k = 0; k < nst; k += 4u) {
+    const uint4 v = row4[k >> 2];
+    uint32_t w0 = funnel_r(v.x, prevw, s), w1 = funnel_r(v.y, v.x, s), w2 = funnel_r(v.z, v.y, s), w3 = funnel_r(v.w, v.z, s);
+    prevw = v.w;
+    if (k == 0u) w0 |= pred;
+    if (k + 4u <= nst) {
+      dst[k] = bswap32(w0); dst[k + 1] = bswap32(w1); dst[k + 2] = bswap32(w2); dst[k + 3] = bswap32(w3);
+    } else {
+      dst[k] = bswap32(w0);
+      if (k + 1u < nst) dst[k + 1] = bswap32(w1);
+      if (k + 2u < nst) dst[k + 2] = bswap32(w2);
+    }
+  }
+#else
+  for (uint32_t k = 0; k < nst; k++) {
+    const uint32_t cur = k < kRowWords ? row[k] : 0u;
+    uint32_t w = funnel_r(cur, prevw, s);
+    prevw = cur;
+    if (k == 0u) w |= pred;
+    dst[k] = bswap32(w);
+  }
+#endif
 }
 
 // swapped-state CRC of one big-endian halfword given as it lies in memory (see crc16_word_sw)

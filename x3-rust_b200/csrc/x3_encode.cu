@@ -814,17 +814,19 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const __grid
 //
 // 128 threads (4 warps) per CTA, one frame at a time, 5 CTAs per SM; one thread owns four consecutive blocks.  CTA 0 is
 // the scanner (scanner_role) that turns published frame sizes into stream offsets.  Per frame:
-//   stage    -- the frame's PCM lands in 176-byte rows (one per thread) by 16-byte cp.async, coalesced on the global
-//               side; it was issued while the previous frame was finishing;
+//   stage    -- the frame's PCM lands in 176-byte rows (one per thread); every warp stages the rows of its own threads
+//               (issued while the previous frame was finishing), so nothing but the warp itself waits for them;
 //   pack     -- every thread codes its strip in place in its own row (single pass, nothing shared);
-//   scan     -- CTA scan of the strips' bit counts; thread 0 publishes the frame size (and does NOT wait for the offset);
-//   relocate -- strips are shifted into one of TWO windows: the finished payload image;
+//   scan     -- CTA scan of the strips' bit counts (barrier 1); thread 0 publishes the frame size -- and nobody waits for
+//               the frame's offset;
+//   relocate -- strips are shifted into one of TWO windows, the finished payload image (barrier 2);
 //   crc      -- 32-byte chunks of the window in parallel (slicing-by-4 tables in shared memory, byte-swapped state),
-//               32 chunks folded per warp by a shuffle tree, slices by Horner, tail and header CRC by one lane;
+//               32 chunks folded per warp by a shuffle tree; warp 0 alone waits for the four warps' slices (named
+//               barrier) and finishes: slices by Horner, tail, header CRC;
 //   out      -- the PREVIOUS frame's window goes to the stream now: its offset (which needs every earlier frame's size)
 //               has had a whole frame time to arrive.  16-byte stores, realigned with PRMT (offsets are only even).
-// A payload larger than a window (9 KiB; only literal / BFP heavy frames) is relocated, summed and written in rounds,
-// after waiting for its own offset.
+// Frames that are not regular -- a payload larger than a window (9 KiB; literal / BFP heavy frames), a strip of less
+// than 32 bits (tiny frames) -- take slow_frame(): merging relocation in rounds, written out at once.
 // ------------------------------------------------------------------------------------------------
 constexpr int NTS = kEncStripThreads;                 // 128
 constexpr uint32_t kWinBytes = 9216;                  // multiple of 1024 (32 chunks of 32 bytes)
@@ -835,16 +837,42 @@ constexpr uint32_t kWinChunks = kWinBytes / 32;
 constexpr uint32_t kMaxSlicesStrip = 32;              // 0x7fe0 / 1024 rounded up
 constexpr uint32_t kRowsBytes = kStripMaxRows * kRowWords * 4;
 
-__device__ __forceinline__ uint32_t crc16_mulc_sw_g(const uint16_t *Tg2, int tbl, uint32_t s_sw) {
-  return (uint32_t)__ldg(Tg2 + tbl * 256 + ((s_sw >> 8) & 0xffu)) ^ (uint32_t)__ldg(Tg2 + (tbl + 1) * 256 + (s_sw & 0xffu));
+// Multiply a byte-swapped CRC state by x^(256 * 2^L) mod P, L = 0..4, with NIBBLE tables in shared memory (4 x 16
+// entries per constant, 640 bytes in all: the byte tables of the bank would cost 5 KB per CTA, and fetching them from
+// global memory put an L2 round trip on every step of the slice tree and of the Horner chain).  The four nibbles are
+// spread into the bytes of one register (two LOP3 and an IMAD); the four table addresses are IDP.4A.
+constexpr int kMulLevels = 5;
+__device__ __forceinline__ void build_mul_tables(uint16_t *s_N, const uint16_t *Tg2, int tid) {
+  // level L multiplies by x^(256 << L): table pairs 8, 10, 12, 14 (x^256 .. x^2048) and 4 (x^4096) of the bank
+  for (int i = tid; i < kMulLevels * 64; i += NTS) {
+    const int L = i >> 6, t = (i >> 4) & 3, nib = i & 15;
+    const int pair = L < 4 ? 8 + 2 * L : 4;
+    // t: 0 = low nibble of the state's high byte ... see crc16_mul_sw
+    const int tbl = t < 2 ? pair : pair + 1;
+    s_N[i] = Tg2[tbl * 256 + ((t & 1) ? nib << 4 : nib)];
+  }
+}
+template <int L>
+__device__ __forceinline__ uint32_t crc16_mul_sw(const uint16_t *s_N, uint32_t s_sw) {
+  // swapped state s_sw = n3 n2 n1 n0 (nibbles); bank: pair[(s_sw >> 8) & 0xff] ^ (pair+1)[s_sw & 0xff]
+  const uint32_t x = (s_sw & 0xf0f0u) * 4096u + (s_sw & 0x0f0fu);   // bytes: n0, n2, n1, n3
+#if defined(__CUDA_ARCH__)
+  const uint32_t tb = (uint32_t)__cvta_generic_to_shared(s_N) + 128u * L;
+  return lds_u16_off<64>(__dp4a(x, 0x00000002u, tb)) ^ lds_u16_off<0>(__dp4a(x, 0x00000200u, tb)) ^
+         lds_u16_off<96>(__dp4a(x, 0x00020000u, tb)) ^ lds_u16_off<32>(__dp4a(x, 0x02000000u, tb));
+#else
+  const uint16_t *N = s_N + 64 * L;
+  return (uint32_t)N[32 + (x & 15u)] ^ (uint32_t)N[(x >> 8) & 15u] ^ (uint32_t)N[48 + ((x >> 16) & 15u)] ^ (uint32_t)N[16 + (x >> 24)];
+#endif
 }
 
-// rows of frame f <- global, this warp's 32 rows (5120 contiguous bytes); n = samples of the frame
+// rows of this warp's 32 threads <- global (5120 contiguous bytes of the frame); n = samples of the frame.
+// Coalesced 16-byte cp.async: chunk c of the warp's region goes to row c / 10, behind the row's 16 bytes of padding.
 __device__ __forceinline__ void stage_rows(const int16_t *frame, uint32_t n, uint32_t *s_rows, uint32_t *s_next, int wid,
                                            int lane) {
   const uint32_t w0 = (uint32_t)wid * 32u * kStripSamples;              // first sample of the warp's rows
   const unsigned char *src = reinterpret_cast<const unsigned char *>(frame + w0);
-  unsigned char *dst = reinterpret_cast<unsigned char *>(s_rows + (uint32_t)wid * 32u * kRowWords);
+  unsigned char *dst = reinterpret_cast<unsigned char *>(s_rows + (uint32_t)wid * 32u * kRowWords + kRowPadWords);
   const uint32_t avail = n > w0 ? n - w0 : 0u;                          // samples of the frame from w0 on
   const uint32_t chunks = avail >> 3;                                   // whole 16-byte chunks
 #pragma unroll
@@ -860,7 +888,7 @@ __device__ __forceinline__ void stage_rows(const int16_t *frame, uint32_t n, uin
       const int16_t v = __ldg(frame + w0 + i);
       if (i < 32u * kStripSamples) {
         const uint32_t r = i / kStripSamples, k = i % kStripSamples;
-        reinterpret_cast<int16_t *>(s_rows + ((uint32_t)wid * 32u + r) * kRowWords)[k] = v;
+        reinterpret_cast<int16_t *>(s_rows + ((uint32_t)wid * 32u + r) * kRowWords + kRowPadWords)[k] = v;
       } else {
         reinterpret_cast<int16_t *>(s_next + 4 * wid)[i - 32u * kStripSamples] = v;
       }
@@ -873,7 +901,7 @@ __device__ __forceinline__ void stage_rows(const int16_t *frame, uint32_t n, uin
 // the payload.  Slice j = the 32 chunks at distance 32j .. 32j+31 from the last whole chunk;
 // V_j ^= sum_l x^(256 l) * crc(chunk at distance 32j + l).  Called by all four warps.
 __device__ __forceinline__ void crc_slices(const uint32_t *win, uint32_t c_lo, uint32_t c_hi, uint32_t nch, uint32_t *s_V,
-                                           const uint16_t *s_T2, const uint16_t *Tg2, int wid, int lane) {
+                                           const uint16_t *s_T2, const uint16_t *s_N, int wid, int lane) {
   if (c_hi <= c_lo) return;
   const uint32_t j_lo = (nch - c_hi) >> 5, j_hi = (nch - 1u - c_lo) >> 5;
   for (uint32_t j = j_lo + (uint32_t)wid; j <= j_hi; j += 4u) {
@@ -895,24 +923,26 @@ __device__ __forceinline__ void crc_slices(const uint32_t *win, uint32_t c_lo, u
         h = crc16_word_sw(s_T2, h, q1.w);
       }
     }
-    h ^= crc16_mulc_sw_g(Tg2, 8, __shfl_down_sync(0xffffffffu, h, 1));     // x^256
-    h ^= crc16_mulc_sw_g(Tg2, 10, __shfl_down_sync(0xffffffffu, h, 2));    // x^512
-    h ^= crc16_mulc_sw_g(Tg2, 12, __shfl_down_sync(0xffffffffu, h, 4));    // x^1024
-    h ^= crc16_mulc_sw_g(Tg2, 14, __shfl_down_sync(0xffffffffu, h, 8));    // x^2048
-    h ^= crc16_mulc_sw_g(Tg2, 4, __shfl_down_sync(0xffffffffu, h, 16));    // x^4096
+    h ^= crc16_mul_sw<0>(s_N, __shfl_down_sync(0xffffffffu, h, 1));     // x^256
+    h ^= crc16_mul_sw<1>(s_N, __shfl_down_sync(0xffffffffu, h, 2));     // x^512
+    h ^= crc16_mul_sw<2>(s_N, __shfl_down_sync(0xffffffffu, h, 4));     // x^1024
+    h ^= crc16_mul_sw<3>(s_N, __shfl_down_sync(0xffffffffu, h, 8));     // x^2048
+    h ^= crc16_mul_sw<4>(s_N, __shfl_down_sync(0xffffffffu, h, 16));    // x^4096
     if (lane == 0) s_V[j] ^= h & 0xffffu;
   }
 }
 
 // One lane: payload CRC from the slice sums (Horner, x^8192 = x^4096 twice) and the bytes after the last whole chunk,
 // which lie in `win` at byte `tail_at`; returns (header CRC << 16) | payload CRC for the frame header.
-__device__ __forceinline__ uint32_t crc_finish(const uint32_t *s_V, const uint32_t *win, uint32_t tail_at, uint32_t payload_len,
-                                               uint32_t n, const uint16_t *s_T2, const uint16_t *Tg2) {
+__device__ __noinline__ uint32_t crc_finish(const uint32_t *s_V, const uint32_t *win, uint32_t tail_at, uint32_t payload_len,
+                                            uint32_t n, const uint16_t *s_T2, const uint16_t *s_N) {
   const uint32_t nch = payload_len >> 5, nsl = (nch + 31u) >> 5;
   uint32_t s = 0;
-  for (int j = (int)nsl - 1; j >= 0; j--) s = crc16_mulc_sw_g(Tg2, 4, crc16_mulc_sw_g(Tg2, 4, s)) ^ s_V[j];
+#pragma unroll 1
+  for (int j = (int)nsl - 1; j >= 0; j--) s = crc16_mul_sw<4>(s_N, crc16_mul_sw<4>(s_N, s)) ^ s_V[j];
   if (nch == 0) s = 0xffffu;
   uint32_t rem = payload_len & 31u, wi = tail_at >> 2;   // rem is even
+#pragma unroll 1
   for (; rem >= 4u; rem -= 4u) s = crc16_word_sw(s_T2, s, win[wi++]);
   if (rem) s = crc16_half_sw(s_T2, s, win[wi] & 0xffffu);
   return (header_crc_sw(s_T2, 1u, n, payload_len) << 16) | bswap16(s);
@@ -932,6 +962,7 @@ __device__ __forceinline__ void copy_window_out(unsigned char *dst, const uint32
   uint4 *d4 = reinterpret_cast<uint4 *>(dst + head);
   const uint32_t w0 = head >> 2;          // first source word
   if ((head & 3u) == 0u) {
+#pragma unroll 1
     for (uint32_t i = tid; i < nvec; i += NTS) {
       const uint32_t *q = s_words + w0 + 4u * i;
       uint4 v;
@@ -939,6 +970,7 @@ __device__ __forceinline__ void copy_window_out(unsigned char *dst, const uint32
       d4[i] = v;
     }
   } else {                                // source starts in the middle of a word
+#pragma unroll 1
     for (uint32_t i = tid; i < nvec; i += NTS) {
       const uint32_t *q = s_words + w0 + 4u * i;
       const uint32_t a0 = q[0], a1 = q[1], a2 = q[2], a3 = q[3], a4 = q[4];
@@ -966,14 +998,100 @@ __device__ __forceinline__ void write_header(unsigned char *out, unsigned long l
   }
 }
 
-// stream offset of frame f: wait for the scanner to turn the published size into a prefix (one thread)
-__device__ __forceinline__ unsigned long long wait_offset(const EncodeArgs &a, uint32_t f, uint32_t frame_bytes, bool &fits) {
-  unsigned long long pv;
-  while (((pv = ld_status(a.status + f)) >> 62) != 2ull) __nanosleep(32);
+// stream offset of frame f: wait for the scanner to turn the published size into a prefix (one thread); the offset
+// goes to slot[0..1], "fits the output buffer" to slot[2]
+__device__ __noinline__ void wait_offset(const EncodeArgs &a, uint32_t f, uint32_t frame_bytes, uint32_t *slot,
+                                         unsigned long long pv = 0) {
+  while ((pv >> 62) != 2ull) {
+    pv = ld_status(a.status + f);
+    if ((pv >> 62) != 2ull) __nanosleep(32);
+  }
   const unsigned long long excl = (pv & kValueMask) - frame_bytes;
-  fits = excl + frame_bytes <= a.out_cap;
+  const bool fits = excl + frame_bytes <= a.out_cap;
   if (!fits) atomicMax(a.result + 1, 1ull);            // ByteWriterInsufficientMemory, bytewriter.rs:88
-  return excl;
+  slot[0] = (uint32_t)excl;
+  slot[1] = (uint32_t)(excl >> 32);
+  slot[2] = fits ? 1u : 0u;
+}
+
+struct StripShared {
+  uint32_t *rows, *win, *next, *V, *misc;
+  const uint16_t *T2, *N;
+};
+// s_misc: [0..4) warp totals, [8] this CTA's next frame, [10..13) offset / fits of the pending frame, [13..16) of a slow
+//         frame, [16..22) stats, [24 + q] header CRC | payload CRC of the frame in window q, [32..160) bit counts of the strips
+
+// The frame waiting in a window: every thread keeps its description in registers (the values are uniform); only the
+// two CRCs, which warp 0 produces late, travel through shared memory (misc[24 + q]).
+struct PendingFrame {
+  uint32_t q;            // window (2 = nothing pending)
+  uint32_t f, n, len;    // frame index, samples, payload bytes
+};
+// the pending frame goes to the stream; its offset is in misc[10..13).  All threads.
+__device__ __forceinline__ void flush_pending(const EncodeArgs &a, const StripShared &S, const PendingFrame &p, int tid) {
+  if (S.misc[12]) {
+    const unsigned long long goff = (unsigned long long)S.misc[10] | ((unsigned long long)S.misc[11] << 32);
+    copy_window_out(a.out + goff + kFrameHeaderLen, S.win + p.q * kWinStride, p.len, tid);
+    if ((tid >> 5) == 1) write_header(a.out, goff, p.n, p.len, S.misc[24 + p.q], tid & 31);
+  }
+}
+
+// A frame that is not regular: merging relocation (strip_relocate) through window 0 in as many rounds as the payload
+// needs, each round summed and written to the stream at once -- which needs the frame's own offset, so the CTA waits
+// for it here (after the pending frame is out).  Returns this CTA's next frame (the ticket is drawn after the wait:
+// a frame that is ticketed but cannot start would hold up every later frame's offset).
+__device__ __noinline__ uint32_t slow_frame(const EncodeArgs &a, const StripShared &S, uint32_t f, uint32_t n, uint32_t T,
+                                            uint32_t O, uint32_t total_bits, const PendingFrame &pend, uint32_t spf, uint32_t last_f,
+                                            uint32_t last_n) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint32_t payload_len = payload_bytes(total_bits), nch = payload_len >> 5;
+  const uint32_t *row = S.rows + (uint32_t)tid * kRowWords;
+  uint32_t *misc = S.misc;
+  if (tid == 32) {
+    if (pend.q < 2u) wait_offset(a, pend.f, (uint32_t)kFrameHeaderLen + pend.len, misc + 10);
+    wait_offset(a, f, (uint32_t)kFrameHeaderLen + payload_len, misc + 13);
+    misc[8] = atomicAdd(a.ticket, 1u);
+  }
+  if (tid < (int)kMaxSlicesStrip) S.V[tid] = 0u;
+  __syncthreads();
+  if (pend.q < 2u) flush_pending(a, S, pend, tid);
+  const unsigned long long goff = (unsigned long long)misc[13] | ((unsigned long long)misc[14] << 32);
+  const bool fits = misc[15] != 0u;
+  const uint32_t f_next = misc[8];
+  uint32_t *win = S.win;
+  __syncthreads();                                   // the pending frame may have been in window 0
+  const uint32_t nrounds = (payload_len + kWinBytes - 1u) / kWinBytes;
+  for (uint32_t r = 0; r < nrounds; r++) {
+    const int32_t wbit0 = (int32_t)(8u * r * kWinBytes);
+    if (tid == 0) {
+      const int32_t zt = (int32_t)total_bits - wbit0;
+      if (zt >= 0 && (zt >> 5) < (int32_t)kWinWords) {
+        win[zt >> 5] = 0u;                           // completed by nobody: tails OR into it
+        win[(zt >> 5) + 1] = 0u;
+      }
+    }
+    uint32_t tail;
+    int32_t tail_idx;
+    strip_relocate(row, T, (int32_t)O - wbit0, win, kWinWords, tail, tail_idx);
+    __syncthreads();
+    if (tail_idx >= 0) atomicOr(&win[tail_idx], tail);
+    if (r == nrounds - 1u && f_next < a.n_frames)
+      stage_rows(a.pcm + (unsigned long long)f_next * spf, f_next == last_f ? last_n : spf, S.rows, S.next, wid, lane);
+    __syncthreads();
+    const uint32_t vb1 = payload_len - r * kWinBytes < kWinBytes ? payload_len - r * kWinBytes : kWinBytes;
+    const uint32_t c_lo = r * kWinChunks, c_hi = nch < (r + 1u) * kWinChunks ? nch : (r + 1u) * kWinChunks;
+    crc_slices(win, c_lo, c_hi, nch, S.V, S.T2, S.N, wid, lane);
+    if (fits) copy_window_out(a.out + goff + kFrameHeaderLen + (size_t)r * kWinBytes, win, vb1, tid);
+    __syncthreads();                                 // window reused by the next round; slice sums complete
+  }
+  if (wid == 0) {
+    uint32_t hw = 0;
+    if (lane == 0) hw = crc_finish(S.V, win, 32u * nch - (nrounds - 1u) * kWinBytes, payload_len, n, S.T2, S.N);
+    hw = __shfl_sync(0xffffffffu, hw, 0);
+    if (fits) write_header(a.out, goff, n, payload_len, hw, lane);
+  }
+  __syncthreads();                                   // the slice sums and window 0 are free again
+  return f_next;
 }
 
 __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __grid_constant__ EncodeArgs a) {
@@ -982,44 +1100,51 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
     return;
   }
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t *s_rows = reinterpret_cast<uint32_t *>(smem_raw);
-  uint32_t *s_win = reinterpret_cast<uint32_t *>(smem_raw + kRowsBytes);                      // 2 windows
-  uint16_t *s_T2 = reinterpret_cast<uint16_t *>(s_win + 2u * kWinStride);
-  uint32_t *s_next = reinterpret_cast<uint32_t *>(s_T2 + 1024);                               // 4 x 16 bytes
-  uint32_t *s_V = s_next + 16;                                                                // kMaxSlicesStrip
-  uint32_t *s_misc = s_V + kMaxSlicesStrip;
-  // s_misc: [0..4) warp totals, [8] this CTA's next frame, [10],[11] stream offset, [12] fits, [16..22) stats,
-  //         per window q at [24 + 4q ..): +0 frame (kNoFrame: nothing pending), +1 samples, +2 payload_len, +3 header CRC | payload CRC
+  StripShared S;
+  S.rows = reinterpret_cast<uint32_t *>(smem_raw);
+  S.win = reinterpret_cast<uint32_t *>(smem_raw + kRowsBytes);                                // 2 windows
+  uint16_t *s_T2 = reinterpret_cast<uint16_t *>(S.win + 2u * kWinStride);
+  S.T2 = s_T2;
+  S.next = reinterpret_cast<uint32_t *>(s_T2 + 1024);                                         // 4 x 16 bytes
+  S.V = S.next + 16;                                                                          // 2 x kMaxSlicesStrip
+  S.misc = S.V + 2 * kMaxSlicesStrip;
+  uint32_t *s_misc = S.misc;
+  uint16_t *s_N = reinterpret_cast<uint16_t *>(s_misc + 160);                                 // kMulLevels x 64 entries
+  S.N = s_N;
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const uint16_t *Tg2 = a.crc_tables + kCrcTableEntries;     // byte-swapped bank (global): tree / Horner constants
+  const uint16_t *Tg2 = a.crc_tables + kCrcTableEntries;     // byte-swapped bank (global)
   for (int i = tid; i < 1024; i += NTS) s_T2[i] = Tg2[i];
+  build_mul_tables(s_N, Tg2, tid);
   if (tid < 6) s_misc[16 + tid] = 0;
-  if (tid == 0) {
-    s_misc[8] = atomicAdd(a.ticket, 1u);
-    s_misc[24] = kNoFrame;
-    s_misc[28] = kNoFrame;
-  }
+  if (tid == 0) s_misc[8] = atomicAdd(a.ticket, 1u);
   __syncthreads();
   const uint32_t spf = a.P.spf;
   const uint32_t last_f = a.n_frames - 1u;
   const uint32_t last_n = (uint32_t)(a.n_samples - (unsigned long long)last_f * spf);
   uint32_t f = s_misc[8];
-  if (f < a.n_frames) stage_rows(a.pcm + (unsigned long long)f * spf, f == last_f ? last_n : spf, s_rows, s_next, wid, lane);
+  if (f < a.n_frames) stage_rows(a.pcm + (unsigned long long)f * spf, f == last_f ? last_n : spf, S.rows, S.next, wid, lane);
   unsigned long long stat_acc = 0;
   uint32_t it = 0, par = 0;
-  uint32_t *row = s_rows + (uint32_t)tid * kRowWords;
+  PendingFrame pend;                                   // the frame not yet written out
+  pend.q = 2u; pend.f = 0; pend.n = 0; pend.len = 0;
+  uint32_t *row = S.rows + (uint32_t)tid * kRowWords;
 
   while (f < a.n_frames) {
     const uint32_t n = f == last_f ? last_n : spf;
     const uint32_t nblk = n > 1 ? (n - 2u) / 20u + 1u : 1u;
+    const uint32_t nstrips = (nblk + kStripBlocks - 1u) / kStripBlocks;
+    // the pending frame's look-back word: asked for now, looked at after the scan (an L2 round trip otherwise sits
+    // between the scan and the window barrier)
+    unsigned long long pend_status = 0;
+    if (tid == 32 && pend.q < 2u) pend_status = ld_status(a.status + pend.f);
     cp_async_wait_all();
-    __syncthreads();                                   // (B0) rows staged; the previous copy-out is complete
+    __syncwarp();                                      // this warp's rows are staged (nobody else touches them)
 
     // ---- local pack ----
     uint32_t T = 0;
     {
-      const uint32_t nxt = lane == 31 ? s_next[4 * wid] : row[kRowWords];
+      const uint32_t nxt = lane == 31 ? S.next[4 * wid] : row[kRowWords + kRowPadWords];
       __syncwarp();                                    // every lane has its look-ahead word before any row changes
       const uint32_t b0 = kStripBlocks * (uint32_t)tid;
       if (b0 < nblk) {
@@ -1046,130 +1171,48 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
       if (lane >= d) incl += t;
     }
     if (lane == 31) s_misc[wid] = incl;
+    s_misc[32 + tid] = T;
+    uint32_t *s_V = S.V + par * kMaxSlicesStrip;
     if (tid >= 32 && tid < 32 + (int)kMaxSlicesStrip) s_V[tid - 32] = 0u;
-    __syncthreads();                                   // (B1)
+    // regular frame: every strip but the last has at least 32 bits (then a window word has at most two owners)
+    const bool regular_strips = __syncthreads_and(T >= 32u || (uint32_t)tid + 1u >= nstrips) != 0;   // (B1)
     const uint32_t w0 = s_misc[0], w1 = s_misc[1], w2 = s_misc[2], w3 = s_misc[3];
     const uint32_t total_bits = w0 + w1 + w2 + w3;
     const uint32_t wbase = (wid > 0 ? w0 : 0u) + (wid > 1 ? w1 : 0u) + (wid > 2 ? w2 : 0u);
     const uint32_t O = wbase + incl - T;
     const uint32_t payload_len = payload_bytes(total_bits);
-    const uint32_t frame_bytes = (uint32_t)kFrameHeaderLen + payload_len;
     const uint32_t nch = payload_len >> 5;             // whole 32-byte CRC chunks
-    uint32_t *win = s_win + par * kWinStride;
-    const uint32_t prev = par ^ 1u;
+    const bool regular = regular_strips && payload_len <= kWinBytes;
     if (tid == 0) {
-      st_status(a.status + f, kFlagAgg | (unsigned long long)frame_bytes);   // publish the size; nobody waits here
-      s_misc[8] = atomicAdd(a.ticket, 1u);
+      // publish the size; nobody waits for the offset here
+      st_status(a.status + f, kFlagAgg | (unsigned long long)((uint32_t)kFrameHeaderLen + payload_len));
+      if (regular) s_misc[8] = atomicAdd(a.ticket, 1u);
     }
 
-    if (payload_len <= kWinBytes) {
-      // ================= the frame fits a window: relocate, sum, and let the PREVIOUS frame go out =================
-      if (tid == 0) {
-        win[total_bits >> 5] = 0u;                     // completed by nobody: tails OR into it
-        win[(total_bits >> 5) + 1] = 0u;               // padding to an even byte count
-      }
-      uint32_t tail;
-      int32_t tail_idx;
-      strip_relocate(row, T, (int32_t)O, win, kWinWords, tail, tail_idx);
-      __syncthreads();                                 // (B3) plain stores done; rows are free
-      if (tail_idx >= 0) atomicOr(&win[tail_idx], tail);
+    if (regular) {
+      uint32_t *win = S.win + par * kWinStride;
+      // the pending frame's offset (published a frame time ago): one thread asks now, everybody knows after (B4)
+      if (tid == 32 && pend.q < 2u) wait_offset(a, pend.f, (uint32_t)kFrameHeaderLen + pend.len, s_misc + 10, pend_status);
+      if ((uint32_t)tid < nstrips)
+        strip_relocate_fast(row, T, O, tid ? s_misc[32 + tid - 1] : 32u, (uint32_t)tid + 1u == nstrips, win);
+      __syncthreads();                                 // (B4) window complete; ticket and pending offset visible
       const uint32_t f_next = s_misc[8];
       if (f_next < a.n_frames)
-        stage_rows(a.pcm + (unsigned long long)f_next * spf, f_next == last_f ? last_n : spf, s_rows, s_next, wid, lane);
-      __syncthreads();                                 // (B4) window complete
-      // offset of the previous frame (published a frame time ago): one thread asks while the others sum this frame
-      uint32_t *pinfo = s_misc + 24 + 4 * prev;
-      const uint32_t pf = pinfo[0];
-      if (tid == 32 && pf != kNoFrame) {
-        bool fits;
-        const unsigned long long excl = wait_offset(a, pf, (uint32_t)kFrameHeaderLen + pinfo[2], fits);
-        s_misc[10] = (uint32_t)excl;
-        s_misc[11] = (uint32_t)(excl >> 32);
-        s_misc[12] = fits ? 1u : 0u;
-      }
-      crc_slices(win, 0u, nch, nch, s_V, s_T2, Tg2, wid, lane);
-      __syncthreads();                                 // (B5) slice CRCs and the previous frame's offset are there
+        stage_rows(a.pcm + (unsigned long long)f_next * spf, f_next == last_f ? last_n : spf, S.rows, S.next, wid, lane);
+      crc_slices(win, 0u, nch, nch, s_V, s_T2, s_N, wid, lane);
       if (wid == 0) {
-        uint32_t hw = 0;
-        if (lane == 0) {
-          hw = crc_finish(s_V, win, 32u * nch, payload_len, n, s_T2, Tg2);
-          uint32_t *info = s_misc + 24 + 4 * par;
-          info[0] = f; info[1] = n; info[2] = payload_len; info[3] = hw;
-        }
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");   // (B5) all slices are there; the other warps only arrive
+        if (lane == 0) s_misc[24 + par] = crc_finish(s_V, win, 32u * nch, payload_len, n, s_T2, s_N);
+      } else {
+        asm volatile("bar.arrive 1, 128;\n" ::: "memory");
       }
-      if (pf != kNoFrame) {
-        if (s_misc[12]) {
-          const unsigned long long goff = (unsigned long long)s_misc[10] | ((unsigned long long)s_misc[11] << 32);
-          copy_window_out(a.out + goff + kFrameHeaderLen, s_win + prev * kWinStride, pinfo[2], tid);
-          if (wid == 1) write_header(a.out, goff, pinfo[1], pinfo[2], pinfo[3], lane);
-        }
-      }
-      // pinfo[0] is overwritten with this slot's next frame two iterations from now (or cleared by the big-frame path)
-      f = f_next;
+      if (pend.q < 2u) flush_pending(a, S, pend, tid);
+      pend.q = par; pend.f = f; pend.n = n; pend.len = payload_len;
       par ^= 1u;
-    } else {
-      // ================= big frame: rounds through window `par`, written out as they come =================
-      __syncthreads();                                 // (C0) ticket visible
-      const uint32_t f_next = s_misc[8];
-      // the pending frame first (stream order is not required, but its window slot and info are reused below)
-      uint32_t *pinfo = s_misc + 24 + 4 * prev;
-      const uint32_t pf = pinfo[0];
-      if (tid == 32) {
-        bool fits;
-        if (pf != kNoFrame) {
-          const unsigned long long excl = wait_offset(a, pf, (uint32_t)kFrameHeaderLen + pinfo[2], fits);
-          s_misc[10] = (uint32_t)excl;
-          s_misc[11] = (uint32_t)(excl >> 32);
-          s_misc[12] = fits ? 1u : 0u;
-        }
-        const unsigned long long excl2 = wait_offset(a, f, frame_bytes, fits);
-        s_misc[13] = (uint32_t)excl2;
-        s_misc[14] = (uint32_t)(excl2 >> 32);
-        s_misc[15] = fits ? 1u : 0u;
-      }
-      __syncthreads();                                 // (C1)
-      if (pf != kNoFrame && s_misc[12]) {
-        const unsigned long long goff = (unsigned long long)s_misc[10] | ((unsigned long long)s_misc[11] << 32);
-        copy_window_out(a.out + goff + kFrameHeaderLen, s_win + prev * kWinStride, pinfo[2], tid);
-        if (wid == 1) write_header(a.out, goff, pinfo[1], pinfo[2], pinfo[3], lane);
-      }
-      const unsigned long long goff = (unsigned long long)s_misc[13] | ((unsigned long long)s_misc[14] << 32);
-      const bool fits = s_misc[15] != 0u;
-      const uint32_t nrounds = (payload_len + kWinBytes - 1u) / kWinBytes;
-      for (uint32_t r = 0; r < nrounds; r++) {
-        const int32_t wbit0 = (int32_t)(8u * r * kWinBytes);
-        if (tid == 0) {
-          const int32_t zt = (int32_t)total_bits - wbit0;
-          if (zt >= 0 && (zt >> 5) < (int32_t)kWinWords) {
-            win[zt >> 5] = 0u;
-            win[(zt >> 5) + 1] = 0u;
-          }
-        }
-        uint32_t tail;
-        int32_t tail_idx;
-        strip_relocate(row, T, (int32_t)O - wbit0, win, kWinWords, tail, tail_idx);
-        __syncthreads();
-        if (tail_idx >= 0) atomicOr(&win[tail_idx], tail);
-        if (r == nrounds - 1u && f_next < a.n_frames)
-          stage_rows(a.pcm + (unsigned long long)f_next * spf, f_next == last_f ? last_n : spf, s_rows, s_next, wid, lane);
-        __syncthreads();
-        const uint32_t vb1 = payload_len - r * kWinBytes < kWinBytes ? payload_len - r * kWinBytes : kWinBytes;
-        const uint32_t c_lo = r * kWinChunks, c_hi = nch < (r + 1u) * kWinChunks ? nch : (r + 1u) * kWinChunks;
-        crc_slices(win, c_lo, c_hi, nch, s_V, s_T2, Tg2, wid, lane);
-        if (fits) copy_window_out(a.out + goff + kFrameHeaderLen + (size_t)r * kWinBytes, win, vb1, tid);
-        __syncthreads();                               // window reused by the next round; slice sums complete
-      }
-      if (wid == 0) {
-        uint32_t hw = 0;
-        if (lane == 0) hw = crc_finish(s_V, win, 32u * nch - (nrounds - 1u) * kWinBytes, payload_len, n, s_T2, Tg2);
-        hw = __shfl_sync(0xffffffffu, hw, 0);
-        if (fits) write_header(a.out, goff, n, payload_len, hw, lane);
-        if (lane == 0) {
-          s_misc[24] = kNoFrame;                       // nothing pending in either window
-          s_misc[28] = kNoFrame;
-        }
-      }
       f = f_next;
+    } else {
+      f = slow_frame(a, S, f, n, T, O, total_bits, pend, spf, last_f, last_n);
+      pend.q = 2u;
     }
     it++;
     if ((it & 127u) == 0u) {                           // the 10-bit counters (4 blocks per frame) are about to fill up
@@ -1183,25 +1226,10 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
   }
   // ---- drain: the last frame of this CTA is still in its window ----
   __syncthreads();
-  {
-    const uint32_t prev = par ^ 1u;
-    uint32_t *pinfo = s_misc + 24 + 4 * prev;
-    const uint32_t pf = pinfo[0];
-    if (pf != kNoFrame) {
-      if (tid == 32) {
-        bool fits;
-        const unsigned long long excl = wait_offset(a, pf, (uint32_t)kFrameHeaderLen + pinfo[2], fits);
-        s_misc[10] = (uint32_t)excl;
-        s_misc[11] = (uint32_t)(excl >> 32);
-        s_misc[12] = fits ? 1u : 0u;
-      }
-      __syncthreads();
-      if (s_misc[12]) {
-        const unsigned long long goff = (unsigned long long)s_misc[10] | ((unsigned long long)s_misc[11] << 32);
-        copy_window_out(a.out + goff + kFrameHeaderLen, s_win + prev * kWinStride, pinfo[2], tid);
-        if (wid == 1) write_header(a.out, goff, pinfo[1], pinfo[2], pinfo[3], lane);
-      }
-    }
+  if (pend.q < 2u) {
+    if (tid == 32) wait_offset(a, pend.f, (uint32_t)kFrameHeaderLen + pend.len, s_misc + 10);
+    __syncthreads();
+    flush_pending(a, S, pend, tid);
   }
 #pragma unroll
   for (int m = 0; m < 6; m++) {
@@ -1230,7 +1258,7 @@ size_t encode_fast_smem_bytes(const CodecParams &P, uint32_t out_words_cap) {
 }
 
 size_t encode_strip_smem_bytes() {
-  return (size_t)kRowsBytes + 2u * kWinStride * 4u + 1024u * 2u + 16u * 4u + kMaxSlicesStrip * 4u + 40u * 4u;
+  return (size_t)kRowsBytes + 2u * kWinStride * 4u + 1024u * 2u + 16u * 4u + 2u * kMaxSlicesStrip * 4u + 160u * 4u + 5u * 64u * 2u;
 }
 
 cudaError_t launch_encode(const EncodeArgs &a, int kind, int grid, size_t smem, cudaStream_t stream) {

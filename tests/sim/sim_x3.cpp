@@ -19,7 +19,7 @@ using namespace x3;
 
 namespace {
 constexpr int NT = 512;
-uint16_t g_T[kCrcBankEntries2];
+uint16_t g_T[kCrcBankEntries3];
 bool g_T_ready = false;
 const uint16_t *T() {
   if (!g_T_ready) { build_crc_bank(g_T); g_T_ready = true; }
@@ -252,25 +252,22 @@ size_t sim_encode_frame_strip(const int16_t *pcm, uint32_t n, const CodecParams 
           uint32_t q[8];
           memcpy(q, win.data() + 8u * (c - c_lo), 32);
           if (c == 0) q[a_off >> 2] ^= 0xffffu << (8u * (a_off & 2u));
-          uint32_t s = 0;
-          for (int w = 0; w < 8; w++) s = crc16_word_sw(t2, s, q[w]);
-          h[lane] = s;
+          // two 16-byte halves, then the lane's own power of x (as crc_slices does)
+          uint32_t h0 = 0, h1 = 0;
+          for (int w = 0; w < 4; w++) { h0 = crc16_word_sw(t2, h0, q[w]); h1 = crc16_word_sw(t2, h1, q[4 + w]); }
+          const uint16_t *N = T() + kCrcBankEntries2;
+          uint32_t hh = crc16_mul_nib(N + 64 * kCrcMulX128, h0) ^ h1;
+          hh = crc16_mul_nib(N + 64 * ((lane >> 2) ? 3 + (lane >> 2) : 0), crc16_mul_nib(N + 64 * (lane & 3), hh));
+          h[lane] = hh;
         }
-        const int tb[5] = {8, 10, 12, 14, 4};
-        for (int k = 0; k < 5; k++) {
-          uint32_t o[32];
-          for (int lane = 0; lane < 32; lane++) o[lane] = lane + (1 << k) < 32 ? h[lane + (1 << k)] : h[lane];
-          for (int lane = 0; lane < 32; lane++)
-            h[lane] ^= (uint32_t)t2[tb[k] * 256 + ((o[lane] >> 8) & 0xffu)] ^ (uint32_t)t2[(tb[k] + 1) * 256 + (o[lane] & 0xffu)];
-        }
+        for (int lane = 1; lane < 32; lane++) h[0] ^= h[lane];
         V[j] ^= h[0] & 0xffffu;
       }
     }
     if (r == nrounds - 1u) {
       const uint32_t nsl = (nch + 31u) >> 5;
       uint32_t s = 0;
-      auto mul4096 = [&](uint32_t x) { return (uint32_t)t2[4 * 256 + ((x >> 8) & 0xffu)] ^ (uint32_t)t2[5 * 256 + (x & 0xffu)]; };
-      for (int j = (int)nsl - 1; j >= 0; j--) s = mul4096(mul4096(s)) ^ V[j];
+      for (int j = (int)nsl - 1; j >= 0; j--) s = crc16_mul_nib(T() + kCrcBankEntries2 + 64 * kCrcMulX8192, s) ^ V[j];
       const uint32_t base = r * win_bytes;
       uint32_t pos = 32u * nch;
       while (pos + 4u <= end_bytes) {

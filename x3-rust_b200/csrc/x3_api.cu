@@ -36,7 +36,7 @@ int cuda_fail(cudaError_t e, const char *what) {
   } while (0)
 
 // ---- CRC table bank (layout in x3_common.cuh) -------------------------------------------------
-uint16_t g_crc_host[kCrcBankEntries2];
+uint16_t g_crc_host[kCrcBankEntries3];
 std::once_flag g_crc_once;
 
 void build_crc_host() { build_crc_bank(g_crc_host); }
@@ -64,8 +64,8 @@ int device_state(DeviceState **out) {
   if (!d.crc_dev) {
     CU(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
     uint16_t *p = nullptr;
-    CU(cudaMalloc(&p, sizeof(uint16_t) * kCrcBankEntries2));
-    CU(cudaMemcpy(p, crc_host(), sizeof(uint16_t) * kCrcBankEntries2, cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&p, sizeof(uint16_t) * kCrcBankEntries3));
+    CU(cudaMemcpy(p, crc_host(), sizeof(uint16_t) * kCrcBankEntries3, cudaMemcpyHostToDevice));
     d.crc_dev = p;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {

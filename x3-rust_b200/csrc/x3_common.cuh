@@ -116,6 +116,15 @@ constexpr int kCrcTableEntries = kCrcTables * 256;
 // A second bank of the same 16 tables with every entry byte-swapped follows the first one in device memory; the
 // fast encoder uses it (crc16_word_sw / crc16_mulc_sw below).
 constexpr int kCrcBankEntries2 = 2 * kCrcTableEntries;
+// A third part follows: NIBBLE tables (4 x 16 entries, byte-swapped state form) of "multiply by a constant mod P" for
+// the strip encoder, which keeps them in shared memory (128 bytes per constant instead of 1 KB).  Constant c:
+//   0: 1 (identity), 1..3: x^(256 c), 4..10: x^(1024 (c-3)), 11: x^128, 12: x^8192.
+// Entry [c*64 + t*16 + nib]: the product for a swapped state whose only non-zero nibble is `nib` at bits 4p..4p+3,
+// p = 2, 3, 0, 1 for t = 0..3 (the order the lookup code wants: crc16_mul_nib).
+constexpr int kCrcMulConsts = 13;
+constexpr int kCrcMulEntries = kCrcMulConsts * 64;
+constexpr int kCrcMulX128 = 11, kCrcMulX8192 = 12;
+constexpr int kCrcBankEntries3 = kCrcBankEntries2 + kCrcMulEntries;
 
 // one 32-bit big-endian word (first stream byte in bits 31..24) through the CRC state
 X3_HD uint32_t crc16_word(const uint16_t *T, uint32_t s, uint32_t w) {
@@ -183,6 +192,18 @@ X3_HD uint32_t crc16_mulc_sw(const uint16_t *T2, uint32_t s_sw) {
 #endif
 }
 X3_HD uint32_t bswap16(uint32_t s) { return ((s & 0xffu) << 8) | ((s >> 8) & 0xffu); }
+// swapped 16-bit state times the constant whose 64-entry nibble table is N (shared memory on the device): the four
+// nibbles are spread into the bytes of one register (two LOP3 and an IMAD), the four table addresses are IDP.4A
+X3_HD uint32_t crc16_mul_nib(const uint16_t *N, uint32_t s_sw) {
+  const uint32_t x = (s_sw & 0xf0f0u) * 4096u + (s_sw & 0x0f0fu);   // bytes: n0, n2, n1, n3
+#if defined(__CUDA_ARCH__)
+  const uint32_t tb = (uint32_t)__cvta_generic_to_shared(N);
+  return lds_u16_off<64>(__dp4a(x, 0x00000002u, tb)) ^ lds_u16_off<0>(__dp4a(x, 0x00000200u, tb)) ^
+         lds_u16_off<96>(__dp4a(x, 0x00020000u, tb)) ^ lds_u16_off<32>(__dp4a(x, 0x02000000u, tb));
+#else
+  return (uint32_t)N[32 + (x & 15u)] ^ (uint32_t)N[(x >> 8) & 15u] ^ (uint32_t)N[48 + ((x >> 16) & 15u)] ^ (uint32_t)N[16 + (x >> 24)];
+#endif
+}
 
 // frame header bytes 0..16 -> header CRC (encoder.rs:153); words are big-endian images of the bytes
 X3_HD uint32_t header_crc(const uint16_t *T, uint32_t id, uint32_t num_samples, uint32_t payload_len) {

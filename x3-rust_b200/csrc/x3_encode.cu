@@ -825,46 +825,17 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const __grid
 //               barrier) and finishes: slices by Horner, tail, header CRC;
 //   out      -- the PREVIOUS frame's window goes to the stream now: its offset (which needs every earlier frame's size)
 //               has had a whole frame time to arrive.  16-byte stores, realigned with PRMT (offsets are only even).
-// Frames that are not regular -- a payload larger than a window (9 KiB; literal / BFP heavy frames), a strip of less
+// Frames that are not regular -- a payload larger than a window (8 KiB; literal / BFP heavy frames), a strip of less
 // than 32 bits (tiny frames) -- take slow_frame(): merging relocation in rounds, written out at once.
 // ------------------------------------------------------------------------------------------------
 constexpr int NTS = kEncStripThreads;                 // 128
-constexpr uint32_t kWinBytes = 9216;                  // multiple of 1024 (32 chunks of 32 bytes)
+constexpr uint32_t kWinBytes = 8192;                  // multiple of 1024 (32 chunks of 32 bytes)
 constexpr uint32_t kWinWords = kWinBytes / 4;
 constexpr uint32_t kWinSlackWords = 8;
 constexpr uint32_t kWinStride = kWinWords + kWinSlackWords;
 constexpr uint32_t kWinChunks = kWinBytes / 32;
 constexpr uint32_t kMaxSlicesStrip = 32;              // 0x7fe0 / 1024 rounded up
 constexpr uint32_t kRowsBytes = kStripMaxRows * kRowWords * 4;
-
-// Multiply a byte-swapped CRC state by x^(256 * 2^L) mod P, L = 0..4, with NIBBLE tables in shared memory (4 x 16
-// entries per constant, 640 bytes in all: the byte tables of the bank would cost 5 KB per CTA, and fetching them from
-// global memory put an L2 round trip on every step of the slice tree and of the Horner chain).  The four nibbles are
-// spread into the bytes of one register (two LOP3 and an IMAD); the four table addresses are IDP.4A.
-constexpr int kMulLevels = 5;
-__device__ __forceinline__ void build_mul_tables(uint16_t *s_N, const uint16_t *Tg2, int tid) {
-  // level L multiplies by x^(256 << L): table pairs 8, 10, 12, 14 (x^256 .. x^2048) and 4 (x^4096) of the bank
-  for (int i = tid; i < kMulLevels * 64; i += NTS) {
-    const int L = i >> 6, t = (i >> 4) & 3, nib = i & 15;
-    const int pair = L < 4 ? 8 + 2 * L : 4;
-    // t: 0 = low nibble of the state's high byte ... see crc16_mul_sw
-    const int tbl = t < 2 ? pair : pair + 1;
-    s_N[i] = Tg2[tbl * 256 + ((t & 1) ? nib << 4 : nib)];
-  }
-}
-template <int L>
-__device__ __forceinline__ uint32_t crc16_mul_sw(const uint16_t *s_N, uint32_t s_sw) {
-  // swapped state s_sw = n3 n2 n1 n0 (nibbles); bank: pair[(s_sw >> 8) & 0xff] ^ (pair+1)[s_sw & 0xff]
-  const uint32_t x = (s_sw & 0xf0f0u) * 4096u + (s_sw & 0x0f0fu);   // bytes: n0, n2, n1, n3
-#if defined(__CUDA_ARCH__)
-  const uint32_t tb = (uint32_t)__cvta_generic_to_shared(s_N) + 128u * L;
-  return lds_u16_off<64>(__dp4a(x, 0x00000002u, tb)) ^ lds_u16_off<0>(__dp4a(x, 0x00000200u, tb)) ^
-         lds_u16_off<96>(__dp4a(x, 0x00020000u, tb)) ^ lds_u16_off<32>(__dp4a(x, 0x02000000u, tb));
-#else
-  const uint16_t *N = s_N + 64 * L;
-  return (uint32_t)N[32 + (x & 15u)] ^ (uint32_t)N[(x >> 8) & 15u] ^ (uint32_t)N[48 + ((x >> 16) & 15u)] ^ (uint32_t)N[16 + (x >> 24)];
-#endif
-}
 
 // rows of this warp's 32 threads <- global (5120 contiguous bytes of the frame); n = samples of the frame.
 // Coalesced 16-byte cp.async: chunk c of the warp's region goes to row c / 10, behind the row's 16 bytes of padding.
@@ -900,8 +871,12 @@ __device__ __forceinline__ void stage_rows(const int16_t *frame, uint32_t n, uin
 // CRC of the whole 32-byte chunks [c_lo, c_hi) of a payload that sit in `win` from chunk c_lo on; nch = whole chunks of
 // the payload.  Slice j = the 32 chunks at distance 32j .. 32j+31 from the last whole chunk;
 // V_j ^= sum_l x^(256 l) * crc(chunk at distance 32j + l).  Called by all four warps.
+// A chunk is summed as two independent 16-byte halves (half the dependent table look-ups in a row; the first half is
+// then multiplied by x^128); lane l multiplies its chunk's sum by x^(256 l) = x^(256 (l & 3)) * x^(1024 (l >> 2)) with
+// its OWN two nibble tables (NA, NB), and the 32 products are XORed by one warp reduction: no shuffle tree.
 __device__ __forceinline__ void crc_slices(const uint32_t *win, uint32_t c_lo, uint32_t c_hi, uint32_t nch, uint32_t *s_V,
-                                           const uint16_t *s_T2, const uint16_t *s_N, int wid, int lane) {
+                                           const uint16_t *s_T2, const uint16_t *s_N, const uint16_t *NA, const uint16_t *NB,
+                                           int wid, int lane) {
   if (c_hi <= c_lo) return;
   const uint32_t j_lo = (nch - c_hi) >> 5, j_hi = (nch - 1u - c_lo) >> 5;
   for (uint32_t j = j_lo + (uint32_t)wid; j <= j_hi; j += 4u) {
@@ -912,34 +887,32 @@ __device__ __forceinline__ void crc_slices(const uint32_t *win, uint32_t c_lo, u
       if (c >= c_lo && c < c_hi) {
         const uint4 *q = reinterpret_cast<const uint4 *>(win) + 2u * (c - c_lo);
         const uint4 q0 = q[0], q1 = q[1];
-        h = c == 0 ? 0xffffu : 0u;   // the CRC's initial value (byte-swapped state form)
-        h = crc16_word_sw(s_T2, h, q0.x);
-        h = crc16_word_sw(s_T2, h, q0.y);
-        h = crc16_word_sw(s_T2, h, q0.z);
-        h = crc16_word_sw(s_T2, h, q0.w);
-        h = crc16_word_sw(s_T2, h, q1.x);
-        h = crc16_word_sw(s_T2, h, q1.y);
-        h = crc16_word_sw(s_T2, h, q1.z);
-        h = crc16_word_sw(s_T2, h, q1.w);
+        uint32_t h0 = c == 0 ? 0xffffu : 0u, h1 = 0u;   // the CRC's initial value (byte-swapped state form)
+        h0 = crc16_word_sw(s_T2, h0, q0.x);
+        h1 = crc16_word_sw(s_T2, h1, q1.x);
+        h0 = crc16_word_sw(s_T2, h0, q0.y);
+        h1 = crc16_word_sw(s_T2, h1, q1.y);
+        h0 = crc16_word_sw(s_T2, h0, q0.z);
+        h1 = crc16_word_sw(s_T2, h1, q1.z);
+        h0 = crc16_word_sw(s_T2, h0, q0.w);
+        h1 = crc16_word_sw(s_T2, h1, q1.w);
+        h = crc16_mul_nib(s_N + 64 * kCrcMulX128, h0) ^ h1;
+        h = crc16_mul_nib(NB, crc16_mul_nib(NA, h));
       }
     }
-    h ^= crc16_mul_sw<0>(s_N, __shfl_down_sync(0xffffffffu, h, 1));     // x^256
-    h ^= crc16_mul_sw<1>(s_N, __shfl_down_sync(0xffffffffu, h, 2));     // x^512
-    h ^= crc16_mul_sw<2>(s_N, __shfl_down_sync(0xffffffffu, h, 4));     // x^1024
-    h ^= crc16_mul_sw<3>(s_N, __shfl_down_sync(0xffffffffu, h, 8));     // x^2048
-    h ^= crc16_mul_sw<4>(s_N, __shfl_down_sync(0xffffffffu, h, 16));    // x^4096
+    h = __reduce_xor_sync(0xffffffffu, h);
     if (lane == 0) s_V[j] ^= h & 0xffffu;
   }
 }
 
-// One lane: payload CRC from the slice sums (Horner, x^8192 = x^4096 twice) and the bytes after the last whole chunk,
+// One lane: payload CRC from the slice sums (Horner in x^8192) and the bytes after the last whole chunk,
 // which lie in `win` at byte `tail_at`; returns (header CRC << 16) | payload CRC for the frame header.
 __device__ __noinline__ uint32_t crc_finish(const uint32_t *s_V, const uint32_t *win, uint32_t tail_at, uint32_t payload_len,
                                             uint32_t n, const uint16_t *s_T2, const uint16_t *s_N) {
   const uint32_t nch = payload_len >> 5, nsl = (nch + 31u) >> 5;
   uint32_t s = 0;
 #pragma unroll 1
-  for (int j = (int)nsl - 1; j >= 0; j--) s = crc16_mul_sw<4>(s_N, crc16_mul_sw<4>(s_N, s)) ^ s_V[j];
+  for (int j = (int)nsl - 1; j >= 0; j--) s = crc16_mul_nib(s_N + 64 * kCrcMulX8192, s) ^ s_V[j];
   if (nch == 0) s = 0xffffu;
   uint32_t rem = payload_len & 31u, wi = tail_at >> 2;   // rem is even
 #pragma unroll 1
@@ -949,9 +922,34 @@ __device__ __noinline__ uint32_t crc_finish(const uint32_t *s_V, const uint32_t 
 }
 
 // payload image (16-byte aligned in shared memory) -> dst (2-byte aligned global address), all NTS threads.
-// Body in 16-byte stores; the shared-memory side is read at a 2- or 4-byte skew and realigned with PRMT.
+// Body in 16-byte stores.  The source of an aligned destination vector starts `head` bytes into the image (even,
+// 0..14): two 16-byte shared loads, five consecutive words picked from the eight (W0 = head / 4), realigned by two
+// bytes with PRMT when SK (head & 2).
+template <int W0, bool SK>
+__device__ __forceinline__ void copy_vectors(uint4 *d4, const uint32_t *s_words, uint32_t nvec, int tid) {
+#pragma unroll 1
+  for (uint32_t i = tid; i < nvec; i += NTS) {
+    const uint4 A = *reinterpret_cast<const uint4 *>(s_words + 4u * i);
+    uint4 B = A;
+    if (W0 != 0 || SK) B = *reinterpret_cast<const uint4 *>(s_words + 4u * i + 4u);
+    const uint32_t x0 = W0 == 0 ? A.x : W0 == 1 ? A.y : W0 == 2 ? A.z : A.w;
+    const uint32_t x1 = W0 == 0 ? A.y : W0 == 1 ? A.z : W0 == 2 ? A.w : B.x;
+    const uint32_t x2 = W0 == 0 ? A.z : W0 == 1 ? A.w : W0 == 2 ? B.x : B.y;
+    const uint32_t x3 = W0 == 0 ? A.w : W0 == 1 ? B.x : W0 == 2 ? B.y : B.z;
+    const uint32_t x4 = W0 == 0 ? B.x : W0 == 1 ? B.y : W0 == 2 ? B.z : B.w;
+    uint4 v;
+    if (SK) {
+      v.x = __byte_perm(x0, x1, 0x5432); v.y = __byte_perm(x1, x2, 0x5432);
+      v.z = __byte_perm(x2, x3, 0x5432); v.w = __byte_perm(x3, x4, 0x5432);
+    } else {
+      v.x = x0; v.y = x1; v.z = x2; v.w = x3;
+    }
+    d4[i] = v;
+  }
+}
 __device__ __forceinline__ void copy_window_out(unsigned char *dst, const uint32_t *s_words, uint32_t L, int tid) {
   uint32_t head = (uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u);  // bytes until dst is 16-byte aligned (even)
+  const uint32_t sel = head >> 1;
   if (head > L) head = L;
   const uint32_t nvec = (L - head) >> 4;
   const uint32_t tail0 = head + (nvec << 4);
@@ -960,25 +958,15 @@ __device__ __forceinline__ void copy_window_out(unsigned char *dst, const uint32
   if ((uint32_t)tid >= 32u && (uint32_t)tid - 32u < ((L - tail0) >> 1))
     reinterpret_cast<uint16_t *>(dst + tail0)[tid - 32] = s16[(tail0 >> 1) + (tid - 32)];
   uint4 *d4 = reinterpret_cast<uint4 *>(dst + head);
-  const uint32_t w0 = head >> 2;          // first source word
-  if ((head & 3u) == 0u) {
-#pragma unroll 1
-    for (uint32_t i = tid; i < nvec; i += NTS) {
-      const uint32_t *q = s_words + w0 + 4u * i;
-      uint4 v;
-      v.x = q[0]; v.y = q[1]; v.z = q[2]; v.w = q[3];
-      d4[i] = v;
-    }
-  } else {                                // source starts in the middle of a word
-#pragma unroll 1
-    for (uint32_t i = tid; i < nvec; i += NTS) {
-      const uint32_t *q = s_words + w0 + 4u * i;
-      const uint32_t a0 = q[0], a1 = q[1], a2 = q[2], a3 = q[3], a4 = q[4];
-      uint4 v;
-      v.x = __byte_perm(a0, a1, 0x5432); v.y = __byte_perm(a1, a2, 0x5432);
-      v.z = __byte_perm(a2, a3, 0x5432); v.w = __byte_perm(a3, a4, 0x5432);
-      d4[i] = v;
-    }
+  switch (sel) {
+    case 0: copy_vectors<0, false>(d4, s_words, nvec, tid); break;
+    case 1: copy_vectors<0, true>(d4, s_words, nvec, tid); break;
+    case 2: copy_vectors<1, false>(d4, s_words, nvec, tid); break;
+    case 3: copy_vectors<1, true>(d4, s_words, nvec, tid); break;
+    case 4: copy_vectors<2, false>(d4, s_words, nvec, tid); break;
+    case 5: copy_vectors<2, true>(d4, s_words, nvec, tid); break;
+    case 6: copy_vectors<3, false>(d4, s_words, nvec, tid); break;
+    default: copy_vectors<3, true>(d4, s_words, nvec, tid); break;
   }
 }
 
@@ -1028,11 +1016,12 @@ struct PendingFrame {
   uint32_t f, n, len;    // frame index, samples, payload bytes
 };
 // the pending frame goes to the stream; its offset is in misc[10..13).  All threads.
-__device__ __forceinline__ void flush_pending(const EncodeArgs &a, const StripShared &S, const PendingFrame &p, int tid) {
+__device__ __forceinline__ void flush_pending(const EncodeArgs &a, const StripShared &S, const PendingFrame &p, int tid,
+                                              int hdr_warp = 1) {
   if (S.misc[12]) {
     const unsigned long long goff = (unsigned long long)S.misc[10] | ((unsigned long long)S.misc[11] << 32);
     copy_window_out(a.out + goff + kFrameHeaderLen, S.win + p.q * kWinStride, p.len, tid);
-    if ((tid >> 5) == 1) write_header(a.out, goff, p.n, p.len, S.misc[24 + p.q], tid & 31);
+    if ((tid >> 5) == hdr_warp) write_header(a.out, goff, p.n, p.len, S.misc[24 + p.q], tid & 31);
   }
 }
 
@@ -1047,6 +1036,7 @@ __device__ __noinline__ uint32_t slow_frame(const EncodeArgs &a, const StripShar
   const uint32_t payload_len = payload_bytes(total_bits), nch = payload_len >> 5;
   const uint32_t *row = S.rows + (uint32_t)tid * kRowWords;
   uint32_t *misc = S.misc;
+  const uint16_t *NA = S.N + 64 * (lane & 3), *NB = S.N + 64 * ((lane >> 2) ? 3 + (lane >> 2) : 0);
   if (tid == 32) {
     if (pend.q < 2u) wait_offset(a, pend.f, (uint32_t)kFrameHeaderLen + pend.len, misc + 10);
     wait_offset(a, f, (uint32_t)kFrameHeaderLen + payload_len, misc + 13);
@@ -1080,7 +1070,7 @@ __device__ __noinline__ uint32_t slow_frame(const EncodeArgs &a, const StripShar
     __syncthreads();
     const uint32_t vb1 = payload_len - r * kWinBytes < kWinBytes ? payload_len - r * kWinBytes : kWinBytes;
     const uint32_t c_lo = r * kWinChunks, c_hi = nch < (r + 1u) * kWinChunks ? nch : (r + 1u) * kWinChunks;
-    crc_slices(win, c_lo, c_hi, nch, S.V, S.T2, S.N, wid, lane);
+    crc_slices(win, c_lo, c_hi, nch, S.V, S.T2, S.N, NA, NB, wid, lane);
     if (fits) copy_window_out(a.out + goff + kFrameHeaderLen + (size_t)r * kWinBytes, win, vb1, tid);
     __syncthreads();                                 // window reused by the next round; slice sums complete
   }
@@ -1109,13 +1099,15 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
   S.V = S.next + 16;                                                                          // 2 x kMaxSlicesStrip
   S.misc = S.V + 2 * kMaxSlicesStrip;
   uint32_t *s_misc = S.misc;
-  uint16_t *s_N = reinterpret_cast<uint16_t *>(s_misc + 160);                                 // kMulLevels x 64 entries
+  uint16_t *s_N = reinterpret_cast<uint16_t *>(s_misc + 160);                                 // kCrcMulEntries
   S.N = s_N;
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const uint16_t *Tg2 = a.crc_tables + kCrcTableEntries;     // byte-swapped bank (global)
   for (int i = tid; i < 1024; i += NTS) s_T2[i] = Tg2[i];
-  build_mul_tables(s_N, Tg2, tid);
+  for (int i = tid; i < kCrcMulEntries; i += NTS) s_N[i] = a.crc_tables[kCrcBankEntries2 + i];
+  // lane l of a slice scales its chunk's sum by x^(256 l): constants (l & 3) and 3 + (l >> 2) of the nibble bank
+  const uint16_t *NA = s_N + 64 * (lane & 3), *NB = s_N + 64 * ((lane >> 2) ? 3 + (lane >> 2) : 0);
   if (tid < 6) s_misc[16 + tid] = 0;
   if (tid == 0) s_misc[8] = atomicAdd(a.ticket, 1u);
   __syncthreads();
@@ -1136,8 +1128,11 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
     const uint32_t nstrips = (nblk + kStripBlocks - 1u) / kStripBlocks;
     // the pending frame's look-back word: asked for now, looked at after the scan (an L2 round trip otherwise sits
     // between the scan and the window barrier)
+    // roles rotate over the warps (warp w of every CTA runs on sub-partition w: a fixed finisher would make one
+    // scheduler the critical path of all frames)
+    const int fin = (int)(it & 3u), pol = (int)((it + 1u) & 3u);
     unsigned long long pend_status = 0;
-    if (tid == 32 && pend.q < 2u) pend_status = ld_status(a.status + pend.f);
+    if (wid == pol && lane == 0 && pend.q < 2u) pend_status = ld_status(a.status + pend.f);
     cp_async_wait_all();
     __syncwarp();                                      // this warp's rows are staged (nobody else touches them)
 
@@ -1192,21 +1187,22 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
     if (regular) {
       uint32_t *win = S.win + par * kWinStride;
       // the pending frame's offset (published a frame time ago): one thread asks now, everybody knows after (B4)
-      if (tid == 32 && pend.q < 2u) wait_offset(a, pend.f, (uint32_t)kFrameHeaderLen + pend.len, s_misc + 10, pend_status);
+      if (wid == pol && lane == 0 && pend.q < 2u)
+        wait_offset(a, pend.f, (uint32_t)kFrameHeaderLen + pend.len, s_misc + 10, pend_status);
       if ((uint32_t)tid < nstrips)
         strip_relocate_fast(row, T, O, tid ? s_misc[32 + tid - 1] : 32u, (uint32_t)tid + 1u == nstrips, win);
       __syncthreads();                                 // (B4) window complete; ticket and pending offset visible
       const uint32_t f_next = s_misc[8];
       if (f_next < a.n_frames)
         stage_rows(a.pcm + (unsigned long long)f_next * spf, f_next == last_f ? last_n : spf, S.rows, S.next, wid, lane);
-      crc_slices(win, 0u, nch, nch, s_V, s_T2, s_N, wid, lane);
-      if (wid == 0) {
+      crc_slices(win, 0u, nch, nch, s_V, s_T2, s_N, NA, NB, wid, lane);
+      if (wid == fin) {
         asm volatile("bar.sync 1, 128;\n" ::: "memory");   // (B5) all slices are there; the other warps only arrive
         if (lane == 0) s_misc[24 + par] = crc_finish(s_V, win, 32u * nch, payload_len, n, s_T2, s_N);
       } else {
         asm volatile("bar.arrive 1, 128;\n" ::: "memory");
       }
-      if (pend.q < 2u) flush_pending(a, S, pend, tid);
+      if (pend.q < 2u) flush_pending(a, S, pend, tid, pol);
       pend.q = par; pend.f = f; pend.n = n; pend.len = payload_len;
       par ^= 1u;
       f = f_next;
@@ -1258,7 +1254,7 @@ size_t encode_fast_smem_bytes(const CodecParams &P, uint32_t out_words_cap) {
 }
 
 size_t encode_strip_smem_bytes() {
-  return (size_t)kRowsBytes + 2u * kWinStride * 4u + 1024u * 2u + 16u * 4u + 2u * kMaxSlicesStrip * 4u + 160u * 4u + 5u * 64u * 2u;
+  return (size_t)kRowsBytes + 2u * kWinStride * 4u + 1024u * 2u + 16u * 4u + 2u * kMaxSlicesStrip * 4u + 160u * 4u + (size_t)kCrcMulEntries * 2u;
 }
 
 cudaError_t launch_encode(const EncodeArgs &a, int kind, int grid, size_t smem, cudaStream_t stream) {

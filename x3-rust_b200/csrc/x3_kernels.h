@@ -35,7 +35,7 @@ struct EncodeArgs {
   unsigned int *ticket;        // zeroed before launch
   unsigned long long *result;  // [0] total bytes, [1] overflow flag, [2..8) stats; zeroed before launch
   unsigned long long *timing;  // 32 words, only written when built with -DX3_ENC_TIMING
-  const uint16_t *crc_tables;  // kCrcBankEntries2 (normal bank, then byte-swapped bank)
+  const uint16_t *crc_tables;  // kCrcBankEntries3 (normal bank, byte-swapped bank, nibble multiply tables)
   int32_t neg_one;             // -1, opaque to the compiler: lets the kernel compute ~x as x*(-1)-1 on the FMA pipe
 };
 

@@ -1006,8 +1006,12 @@ struct StripShared {
   uint32_t *rows, *win, *next, *V, *misc;
   const uint16_t *T2, *N;
 };
-// s_misc: [0..4) warp totals, [8] this CTA's next frame, [10..13) offset / fits of the pending frame, [13..16) of a slow
-//         frame, [16..22) stats, [24 + q] header CRC | payload CRC of the frame in window q, [32..160) bit counts of the strips
+// s_misc: [0..4) warp totals, [4 + p] bits of the frame, [6 + p] this CTA's next frame (p = iteration parity: values
+//         read after the window barrier of one iteration may be rewritten early in the next), [8] next frame (slow path),
+//         [10..13) / [13..16) offset and fits of the pending / of the slow frame (slow path), [16..22) stats,
+//         [24 + q] header CRC | payload CRC of the frame in window q, [32 + 4p ..) offset and fits of the pending frame,
+//         [48..50) mbarrier "window flushed", [64..192) bit counts of the strips
+constexpr int kMiscT = 64, kMiscWords = 192;
 
 // The frame waiting in a window: every thread keeps its description in registers (the values are uniform); only the
 // two CRCs, which warp 0 produces late, travel through shared memory (misc[24 + q]).
@@ -1017,9 +1021,9 @@ struct PendingFrame {
 };
 // the pending frame goes to the stream; its offset is in misc[10..13).  All threads.
 __device__ __forceinline__ void flush_pending(const EncodeArgs &a, const StripShared &S, const PendingFrame &p, int tid,
-                                              int hdr_warp = 1) {
-  if (S.misc[12]) {
-    const unsigned long long goff = (unsigned long long)S.misc[10] | ((unsigned long long)S.misc[11] << 32);
+                                              const uint32_t *slot, int hdr_warp = 1) {
+  if (slot[2]) {
+    const unsigned long long goff = (unsigned long long)slot[0] | ((unsigned long long)slot[1] << 32);
     copy_window_out(a.out + goff + kFrameHeaderLen, S.win + p.q * kWinStride, p.len, tid);
     if ((tid >> 5) == hdr_warp) write_header(a.out, goff, p.n, p.len, S.misc[24 + p.q], tid & 31);
   }
@@ -1044,7 +1048,7 @@ __device__ __noinline__ uint32_t slow_frame(const EncodeArgs &a, const StripShar
   }
   if (tid < (int)kMaxSlicesStrip) S.V[tid] = 0u;
   __syncthreads();
-  if (pend.q < 2u) flush_pending(a, S, pend, tid);
+  if (pend.q < 2u) flush_pending(a, S, pend, tid, misc + 10);
   const unsigned long long goff = (unsigned long long)misc[13] | ((unsigned long long)misc[14] << 32);
   const bool fits = misc[15] != 0u;
   const uint32_t f_next = misc[8];
@@ -1099,7 +1103,7 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
   S.V = S.next + 16;                                                                          // 2 x kMaxSlicesStrip
   S.misc = S.V + 2 * kMaxSlicesStrip;
   uint32_t *s_misc = S.misc;
-  uint16_t *s_N = reinterpret_cast<uint16_t *>(s_misc + 160);                                 // kCrcMulEntries
+  uint16_t *s_N = reinterpret_cast<uint16_t *>(s_misc + kMiscWords);                                 // kCrcMulEntries
   S.N = s_N;
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -1109,7 +1113,11 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
   // lane l of a slice scales its chunk's sum by x^(256 l): constants (l & 3) and 3 + (l >> 2) of the nibble bank
   const uint16_t *NA = s_N + 64 * (lane & 3), *NB = s_N + 64 * ((lane >> 2) ? 3 + (lane >> 2) : 0);
   if (tid < 6) s_misc[16 + tid] = 0;
-  if (tid == 0) s_misc[8] = atomicAdd(a.ticket, 1u);
+  const uint32_t mb_flush = (uint32_t)__cvta_generic_to_shared(s_misc + 48);   // one arrival per warp and iteration
+  if (tid == 0) {
+    s_misc[8] = atomicAdd(a.ticket, 1u);
+    mbar_init(mb_flush, 4);
+  }
   __syncthreads();
   const uint32_t spf = a.P.spf;
   const uint32_t last_f = a.n_frames - 1u;
@@ -1158,7 +1166,10 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
       }
     }
 
-    // ---- CTA scan of the strips' bit counts ----
+    // ---- scan of the strips' bit counts: within the warp by shuffles, across warps by a CHAIN of named barriers --
+    // warp w signals "my total is there" and waits only for the warps before it, so an early warp relocates while a
+    // late one is still packing (a CTA-wide barrier here cost 15 % of the kernel: the four warps sit on four
+    // different schedulers and rarely finish together) ----
     uint32_t incl = T;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -1166,33 +1177,60 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
       if (lane >= d) incl += t;
     }
     if (lane == 31) s_misc[wid] = incl;
-    s_misc[32 + tid] = T;
+    s_misc[kMiscT + tid] = T;
     uint32_t *s_V = S.V + par * kMaxSlicesStrip;
     if (tid >= 32 && tid < 32 + (int)kMaxSlicesStrip) s_V[tid - 32] = 0u;
-    // regular frame: every strip but the last has at least 32 bits (then a window word has at most two owners)
-    const bool regular_strips = __syncthreads_and(T >= 32u || (uint32_t)tid + 1u >= nstrips) != 0;   // (B1)
-    const uint32_t w0 = s_misc[0], w1 = s_misc[1], w2 = s_misc[2], w3 = s_misc[3];
-    const uint32_t total_bits = w0 + w1 + w2 + w3;
-    const uint32_t wbase = (wid > 0 ? w0 : 0u) + (wid > 1 ? w1 : 0u) + (wid > 2 ? w2 : 0u);
+    uint32_t wbase = 0;
+    if (wid == 0) {
+      asm volatile("bar.arrive 2, 128;\n" ::: "memory");
+    } else if (wid == 1) {
+      asm volatile("bar.arrive 3, 96;\n" ::: "memory");
+      asm volatile("bar.sync 2, 128;\n" ::: "memory");
+      wbase = s_misc[0];
+    } else if (wid == 2) {
+      asm volatile("bar.arrive 4, 64;\n" ::: "memory");
+      asm volatile("bar.sync 2, 128;\n" ::: "memory");
+      asm volatile("bar.sync 3, 96;\n" ::: "memory");
+      wbase = s_misc[0] + s_misc[1];
+    } else {
+      asm volatile("bar.sync 2, 128;\n" ::: "memory");
+      asm volatile("bar.sync 3, 96;\n" ::: "memory");
+      asm volatile("bar.sync 4, 64;\n" ::: "memory");
+      wbase = s_misc[0] + s_misc[1] + s_misc[2];
+    }
     const uint32_t O = wbase + incl - T;
+    uint32_t *win = S.win + par * kWinStride;
+    // The last warp knows the frame's size first: it publishes it (nobody waits for the offset here), decides whether
+    // the frame is regular, and draws the CTA's next frame -- the ticket is consumed after the window barrier, so the
+    // atomic's round trip hides behind the relocation.  (A strip that is not the frame's last always holds four whole
+    // blocks, at least 88 bits: "regular" is only a question of size.)
+    uint32_t ticket = 0;
+    if (tid == NTS - 1) {
+      const uint32_t tb = wbase + incl;
+      const uint32_t pl = payload_bytes(tb);
+      st_status(a.status + f, kFlagAgg | (unsigned long long)((uint32_t)kFrameHeaderLen + pl));
+      s_misc[4 + (it & 1u)] = tb;
+      if (pl <= kWinBytes) ticket = atomicAdd(a.ticket, 1u);
+    }
+    // the pending frame's offset (published a frame time ago): one thread asks, everybody knows after (B4)
+    uint32_t *off_slot = s_misc + 32 + 4 * (it & 1u);
+    if (wid == pol && lane == 0 && pend.q < 2u)
+      wait_offset(a, pend.f, (uint32_t)kFrameHeaderLen + pend.len, off_slot, pend_status);
+    // The window about to be written is the one the previous iteration copied out at its end: every warp has said
+    // "my share is out" on an mbarrier since (a split barrier: the arrival was a whole pack phase ago, so nobody waits).
+    if (it) mbar_wait(mb_flush, (it - 1u) & 1u);
+    // relocation, before the frame is known to fit the window: a strip that would leave it stays where it is (the
+    // frame then takes the slow path, which starts over from the rows)
+    if ((uint32_t)tid < nstrips && ((O + T + 31u) >> 5) <= kWinWords)
+      strip_relocate_fast(row, T, O, tid ? s_misc[kMiscT + tid - 1] : 32u, (uint32_t)tid + 1u == nstrips, win);
+    if (tid == NTS - 1) s_misc[6 + (it & 1u)] = ticket;
+    __syncthreads();                                   // (B4) window complete; size, ticket and pending offset visible
+    const uint32_t total_bits = s_misc[4 + (it & 1u)];
     const uint32_t payload_len = payload_bytes(total_bits);
     const uint32_t nch = payload_len >> 5;             // whole 32-byte CRC chunks
-    const bool regular = regular_strips && payload_len <= kWinBytes;
-    if (tid == 0) {
-      // publish the size; nobody waits for the offset here
-      st_status(a.status + f, kFlagAgg | (unsigned long long)((uint32_t)kFrameHeaderLen + payload_len));
-      if (regular) s_misc[8] = atomicAdd(a.ticket, 1u);
-    }
 
-    if (regular) {
-      uint32_t *win = S.win + par * kWinStride;
-      // the pending frame's offset (published a frame time ago): one thread asks now, everybody knows after (B4)
-      if (wid == pol && lane == 0 && pend.q < 2u)
-        wait_offset(a, pend.f, (uint32_t)kFrameHeaderLen + pend.len, s_misc + 10, pend_status);
-      if ((uint32_t)tid < nstrips)
-        strip_relocate_fast(row, T, O, tid ? s_misc[32 + tid - 1] : 32u, (uint32_t)tid + 1u == nstrips, win);
-      __syncthreads();                                 // (B4) window complete; ticket and pending offset visible
-      const uint32_t f_next = s_misc[8];
+    if (payload_len <= kWinBytes) {
+      const uint32_t f_next = s_misc[6 + (it & 1u)];
       if (f_next < a.n_frames)
         stage_rows(a.pcm + (unsigned long long)f_next * spf, f_next == last_f ? last_n : spf, S.rows, S.next, wid, lane);
       crc_slices(win, 0u, nch, nch, s_V, s_T2, s_N, NA, NB, wid, lane);
@@ -1202,7 +1240,7 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
       } else {
         asm volatile("bar.arrive 1, 128;\n" ::: "memory");
       }
-      if (pend.q < 2u) flush_pending(a, S, pend, tid, pol);
+      if (pend.q < 2u) flush_pending(a, S, pend, tid, off_slot, pol);
       pend.q = par; pend.f = f; pend.n = n; pend.len = payload_len;
       par ^= 1u;
       f = f_next;
@@ -1210,6 +1248,8 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
       f = slow_frame(a, S, f, n, T, O, total_bits, pend, spf, last_f, last_n);
       pend.q = 2u;
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(mb_flush);              // this warp is done with the windows of this iteration
     it++;
     if ((it & 127u) == 0u) {                           // the 10-bit counters (4 blocks per frame) are about to fill up
 #pragma unroll
@@ -1225,7 +1265,7 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
   if (pend.q < 2u) {
     if (tid == 32) wait_offset(a, pend.f, (uint32_t)kFrameHeaderLen + pend.len, s_misc + 10);
     __syncthreads();
-    flush_pending(a, S, pend, tid);
+    flush_pending(a, S, pend, tid, s_misc + 10);
   }
 #pragma unroll
   for (int m = 0; m < 6; m++) {
@@ -1254,7 +1294,7 @@ size_t encode_fast_smem_bytes(const CodecParams &P, uint32_t out_words_cap) {
 }
 
 size_t encode_strip_smem_bytes() {
-  return (size_t)kRowsBytes + 2u * kWinStride * 4u + 1024u * 2u + 16u * 4u + 2u * kMaxSlicesStrip * 4u + 160u * 4u + (size_t)kCrcMulEntries * 2u;
+  return (size_t)kRowsBytes + 2u * kWinStride * 4u + 1024u * 2u + 16u * 4u + 2u * kMaxSlicesStrip * 4u + (size_t)kMiscWords * 4u + (size_t)kCrcMulEntries * 2u;
 }
 
 cudaError_t launch_encode(const EncodeArgs &a, int kind, int grid, size_t smem, cudaStream_t stream) {

@@ -460,6 +460,11 @@ int sim_decode_frame(const uint8_t *stream, size_t stream_len, size_t pos, uint3
     for (uint32_t f = 0; f < 4; f++) par[f] = rice_block_par(f);
     r = decode_frame_fast(rd, payload_len, out, samples, stage, 1u, inv, par);
     if (r == kDecOk) *used_fast = 1;
+  } else if (mode == 0) {   // every other frame: the generic fast path
+    PlainBitReader rd;
+    rd.init(pl, stream + stream_len);
+    r = decode_frame_generic(rd, payload_len, out, samples, P);
+    if (r == kDecOk) *used_fast = 2;
   }
   if (r == kDecRetryExact) r = decode_frame_exact(pl, payload_len, out, samples, P);
   return r;

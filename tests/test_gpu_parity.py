@@ -426,3 +426,79 @@ def test_c5_files_match_oracle(pkg, dev, oracle, file_index):
     assert length == ref.size and stats == rstats and np.array_equal(out[:length].cpu().numpy(), ref)
     dec, ns, res, code = dev.decode_tensor(out, length, p, max_samples=n)
     assert code == 0 and ns == n and res.frames == 5760 and torch.equal(dec[:n], pcm)
+
+
+# ---------------------------------------------------------------------------------------------------
+# round 2: parity gaps named by the round-1 review
+# ---------------------------------------------------------------------------------------------------
+def test_golden_encode_block_ftype3_through_gpu(pkg, golden):
+    """encoder.rs:520-563 (test_x3_encode_block_ftype3: a Rice-3 block written after a 1-bit lead): the block's bits
+    as the GPU encoder emits them inside a frame (behind the 16-bit first sample) equal the reference's."""
+    g = golden["test_x3_encode_block_ftype3"]
+    p = pkg.x3.Parameters.default()
+    data, _ = pkg.encoder.encode_array(np.array(g["wav"], dtype=np.int16), p)
+    bits = "".join("{:08b}".format(b) for b in bytes(data[20:]))[16:]
+    exp = "".join("{:08b}".format(b) for b in g["expected"])[g["lead_zero_bits"]:]   # the vector starts with the lead bit
+    n = min(len(bits), len(exp))
+    assert bits[:n] == exp[:n] and set(bits[n:] + exp[n:]) <= {"0"}
+
+
+@pytest.mark.parametrize("bpf", [1, 4, 10])
+def test_small_frames_large_stream_round_trip(pkg, dev, oracle, bpf):
+    """Streams of very small frames (blocks_per_frame 1, 4, 10: 22 .. ~120 bytes per frame) on 5 M samples overflow
+    the default frame table (sized for >= 256-byte frames) and the 1024 candidates per 128 KiB tile of the index; the
+    decoder must then retry with small tiles and a full-size table, not report an error the reference does not have
+    (decoder.rs:49-55 trusts header.samples for any frame size)."""
+    import torch
+    n = 5000000
+    p, po = mk_params(pkg, oracle, bpf=bpf)
+    pcm = dev.synth(2, 0x58330002, 384000, 384000 - 1000000, n)
+    out, length, stats = dev.encode_tensor(pcm, p)
+    head = 200000
+    ref, _ = oracle.encode(pcm[:head].cpu().numpy(), po)
+    assert np.array_equal(out[:ref.size].cpu().numpy(), ref)           # byte parity on a prefix (whole frames)
+    dec, ns, res, code = dev.decode_tensor(out, length, p, max_samples=n)
+    assert code == 0 and ns == n and res.frames == (n + 20 * bpf - 1) // (20 * bpf)
+    assert torch.equal(dec[:n], pcm)
+
+
+@pytest.mark.parametrize("shards", [2, 3, 8])
+def test_sharded_cuda_encode_equals_single_stream(pkg, dev, oracle, shards):
+    """SURVEY 8(e) with the CUDA encoder: a recording cut into G frame-range shards (sharding.shard_frames), every
+    shard encoded by x3_encode_device on its own, the shard streams placed at the offsets exchange_sizes would hand
+    out -- the concatenation must be the oracle's single stream of the whole signal, byte for byte."""
+    import torch
+    sharding = importlib.import_module("x3-rust_b200.sharding")
+    p = pkg.x3.Parameters.default()
+    n = 1234567                                   # 124 frames, the last one short
+    pcm = dev.synth(2, 0x58330002, 384000, 2 * 384000 - 600000, n)
+    ref, rstats = oracle.encode(pcm.cpu().numpy(), threads=8)
+    parts, sizes, stats_sum = [], [], [0] * 6
+    for r in range(shards):
+        s0, s1 = sharding.shard_frames(n, 10000, r, shards)
+        out, length, stats = dev.encode_tensor(pcm[s0:s1].clone(), p)
+        parts.append(out[:length])
+        sizes.append(length)
+        stats_sum = [a + b for a, b in zip(stats_sum, stats)]
+    whole = torch.empty(sum(sizes), dtype=torch.uint8, device="cuda")
+    for r in range(shards):
+        base = sum(sizes[:r])                     # = exchange_sizes(...)[1] on rank r
+        whole[base:base + sizes[r]] = parts[r]
+    assert whole.numel() == ref.size and np.array_equal(whole.cpu().numpy(), ref) and stats_sum == rstats
+
+
+def test_c5_dealt_files_first_and_last_frames(pkg, dev, oracle):
+    """SURVEY 8(d), C5 subset: first and last frame of every 64th file (plus the files deal_files hands to a rank of an
+    8-GPU run): GPU frame bytes equal the oracle's.  Files are encoded on the GPU from their first and last 20 000
+    samples' worth of frames -- frames are independent, so a frame's bytes do not depend on the rest of its file."""
+    sharding = importlib.import_module("x3-rust_b200.sharding")
+    p = pkg.x3.Parameters.default()
+    n_file, spf = 57600000, 10000
+    dealt = sharding.deal_files([n_file // spf] * 1024, 8)
+    assert [len(d) for d in dealt] == [128] * 8 and dealt[3][0] == 384
+    for fi in list(range(0, 1024, 64)) + [dealt[7][-1]]:
+        for n0 in (0, n_file - spf):
+            pcm = dev.synth(2, 0x58330005 + fi, 96000, n0, spf)
+            out, length, _ = dev.encode_tensor(pcm, p)
+            ref, _ = oracle.encode(oracle.synth(2, 0x58330005 + fi, 96000, n0, spf))
+            assert length == ref.size and np.array_equal(out[:length].cpu().numpy(), ref), (fi, n0)

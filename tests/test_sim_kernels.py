@@ -190,14 +190,15 @@ def test_sim_decode_misaligned_payload(sim, oracle):
         assert np.array_equal(got, pcm[:20000]) and fast == 2
 
 
-def test_sim_exact_matches_oracle_on_malformed(sim, oracle):
-    """Random bit flips inside payloads: the kernel policy (fast, then exact on doubt) must report exactly
-    what the oracle's literal BitReader port reports, sample for sample."""
+@pytest.mark.parametrize("n,p8", [(10000, P8()), (9987, P8()), (9000, P8(16, 600)), (9000, P8(20, 500, (0, 2, 3), (3, 8, 18)))])
+def test_sim_exact_matches_oracle_on_malformed(sim, oracle, n, p8):
+    """Random bit flips inside payloads: the kernel policy (tuned or generic fast path, then exact on doubt) must report
+    exactly what the oracle's literal BitReader port reports, sample for sample."""
     rng = np.random.default_rng(3)
     base = signals(oracle)
     for name in ("s2a", "s4", "small", "s1"):
-        pcm = base[name][:10000]
-        stream, _ = oracle.encode(pcm)
+        pcm = base[name][:n]
+        stream, _ = oracle.encode(pcm, oparams(oracle, p8))
         (pos, samples, plen), = walk(oracle, stream)
         for trial in range(60):
             s = stream.copy()
@@ -211,7 +212,7 @@ def test_sim_exact_matches_oracle_on_malformed(sim, oracle):
                 pl = plen
             # oracle verdict on the bare payload
             try:
-                ref = oracle.decode_frame(bytes(s[20:20 + pl]), samples)
+                ref = oracle.decode_frame(bytes(s[20:20 + pl]), samples, oparams(oracle, p8))
                 ref_rc = 0
             except oracle.OracleError as e:
                 ref, ref_rc = None, e.code
@@ -220,7 +221,7 @@ def test_sim_exact_matches_oracle_on_malformed(sim, oracle):
             out = raw[shift:shift + samples]
             uf = C.c_int()
             rc = sim.sim_decode_frame(s.ctypes.data_as(C.c_void_p), C.c_size_t(s.size), C.c_size_t(0),
-                                      C.c_uint32(samples), C.c_uint32(pl), P8().ctypes.data_as(C.c_void_p),
+                                      C.c_uint32(samples), C.c_uint32(pl), p8.ctypes.data_as(C.c_void_p),
                                       C.c_void_p(out.ctypes.data), C.c_int(0), C.byref(uf))
             assert rc == ref_rc, (name, trial, rc, ref_rc)
             if ref_rc == 0:

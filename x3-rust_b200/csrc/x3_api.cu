@@ -654,8 +654,29 @@ int host_walk(const uint8_t *s, size_t len, std::vector<FrameRec> &frames, unsig
 namespace {
 // x3_decode_device; `consumed` (optional) receives the stream bytes covered by the frames found when the device
 // index was used and proven (0 otherwise)
+constexpr int kRetryLargerTable = 1000;   // internal: the frame table / tile candidate capacity was too small
+int decode_device_attempt(const uint8_t *d_frames, size_t len, const x3_params *p, int16_t *d_pcm, size_t pcm_cap,
+                          size_t *n_out, x3_decode_result *res, void *cuda_stream, unsigned long long *consumed,
+                          uint32_t tile_bytes, unsigned long long max_frames);
+
+// The frame table is sized for frames of 256 bytes and more (the default frame is ~4.7 KB) and the index scans 128 KiB
+// tiles with room for 1024 candidates each.  A stream of smaller frames (small blocks_per_frame: the reference accepts
+// any, decoder.rs:49-55) overflows one or the other; it is then decoded again with 16 KiB tiles and a table for the
+// smallest frame there is (20 + 2 bytes).
 int decode_device_impl(const uint8_t *d_frames, size_t len, const x3_params *p, int16_t *d_pcm, size_t pcm_cap,
                        size_t *n_out, x3_decode_result *res, void *cuda_stream, unsigned long long *consumed) {
+  unsigned long long max_frames = len / 256 + 4096;
+  const unsigned long long most = len / 22 + 1;
+  if (max_frames > most) max_frames = most;
+  int rc = decode_device_attempt(d_frames, len, p, d_pcm, pcm_cap, n_out, res, cuda_stream, consumed, kScanTileBytes, max_frames);
+  if (rc == kRetryLargerTable)
+    rc = decode_device_attempt(d_frames, len, p, d_pcm, pcm_cap, n_out, res, cuda_stream, consumed, kScanTileBytesSmall, most);
+  return rc;
+}
+
+int decode_device_attempt(const uint8_t *d_frames, size_t len, const x3_params *p, int16_t *d_pcm, size_t pcm_cap,
+                          size_t *n_out, x3_decode_result *res, void *cuda_stream, unsigned long long *consumed,
+                          uint32_t tile_bytes, unsigned long long max_frames) {
   if (consumed) *consumed = 0;
   Derived d;
   int rc = derive(p, &d);
@@ -684,9 +705,8 @@ int decode_device_impl(const uint8_t *d_frames, size_t len, const x3_params *p, 
   unsigned long long *host_res;
   if ((rc = pinned(&host_res))) return rc;
 
-  const uint32_t n_tiles = (uint32_t)((len + kScanTileBytes - 1) / kScanTileBytes);
-  unsigned long long max_frames = len / 256 + 4096;
-  if (max_frames > len / 22 + 1) max_frames = len / 22 + 1;
+  const uint32_t n_tiles = (uint32_t)((len + tile_bytes - 1) / tile_bytes);
+  const bool can_retry = tile_bytes != kScanTileBytesSmall;
   // workspace layout
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
@@ -716,6 +736,7 @@ int decode_device_impl(const uint8_t *d_frames, size_t len, const x3_params *p, 
   sa.result = reinterpret_cast<unsigned long long *>(ws + o_res);
   sa.crc_tables = ds->crc_dev;
   sa.n_tiles = n_tiles;
+  sa.tile_bytes = tile_bytes;
 
   DecodeArgs da;
   da.stream = d_frames;
@@ -779,6 +800,10 @@ int decode_device_impl(const uint8_t *d_frames, size_t len, const x3_params *p, 
     if (e == cudaSuccess) e = cudaMemcpyAsync(host_res + 8, ws + o_dres, 8, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return fail(e, "decode (device index)");
+    if ((host_res[2] & 2ull) != 0 && can_retry) {  // a capacity was exceeded: smaller tiles, larger table
+      cudaFreeAsync(ws, st);
+      return kRetryLargerTable;
+    }
     if (host_res[2] != 0) need_walk = true;  // the table could not be proven equal to the reference's walk
     n_frames = host_res[4];
     total_samples = host_res[5];
@@ -801,7 +826,7 @@ int decode_device_impl(const uint8_t *d_frames, size_t len, const x3_params *p, 
     n_frames = frames.size();
     if (n_frames > max_frames) {
       cudaFreeAsync(ws, st);
-      return X3_ERR_UNSUPPORTED_PARAMS;
+      return can_retry ? kRetryLargerTable : X3_ERR_UNSUPPORTED_PARAMS;   // the retry's table holds any stream
     }
     host_res[4] = n_frames;
     e = cudaMemcpyAsync(ws + o_res + 32, host_res + 4, 8, cudaMemcpyHostToDevice, st);

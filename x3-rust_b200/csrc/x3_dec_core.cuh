@@ -468,4 +468,112 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
   return kDecOk;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Generic fast path: any Parameters (block_len, codes) and any number of samples, same Reader concept, one sample at a
+// time: no unrolling by block shape, no sector staging (samples leave in 4-byte stores where the address allows, else
+// 2-byte stores).  Slower than decode_frame_fast, an order of magnitude faster than the exact path (which reads the
+// payload bytewise and is only meant to settle malformed frames).  Same contract: whatever it cannot prove well
+// formed makes it give up (kDecRetryExact) and the exact path decides what the reference would have reported.
+// The Rice index is computed, not looked up: i = z (ftype 1) or r + level * (z - 1) (decoder.rs:157-165, :184-191),
+// delta = INV_RICE_CODE[i] in closed form (x3.rs:200-204).
+// ------------------------------------------------------------------------------------------------
+template <class Reader>
+X3_HD int decode_frame_generic(Reader &rd, uint32_t payload_len, int16_t *out, uint32_t samples, const CodecParams &P) {
+  uint32_t hi, lo;
+  rd.block_begin();
+  rd.window(hi, lo);
+  int32_t lw = (int32_t)(int16_t)(hi >> 16);   // first sample, decoder.rs:42
+  rd.advance(16);
+  // pairing for 4-byte stores: `held` is the sample at the even (4-byte aligned) position before the current one
+  uint32_t p = 0;
+  uint32_t held = 0;
+  bool have_held = false;
+#define X3_GEN_EMIT(v)                                                                         \
+  {                                                                                            \
+    const uint32_t s16 = (uint32_t)(v) & 0xffffu;                                              \
+    if ((((uintptr_t)(out + p)) & 2u) == 0u) {                                                 \
+      held = s16;                                                                              \
+      have_held = true;                                                                        \
+    } else if (have_held) {                                                                    \
+      *reinterpret_cast<uint32_t *>(out + p - 1) = held | (s16 << 16);                         \
+      have_held = false;                                                                       \
+    } else {                                                                                   \
+      out[p] = (int16_t)s16;                                                                   \
+    }                                                                                          \
+    p++;                                                                                       \
+  }
+  X3_GEN_EMIT(lw)
+  uint32_t remaining = samples - 1u;
+  // The reader is topped up every 16 to 32 samples (<= 66 bytes of payload), never twice in a row: a top-up waits for
+  // the copies of the one before it, so two in quick succession would wait out a whole memory round trip.
+  uint32_t since = 16u;
+  while (remaining > 0u) {
+    const uint32_t bl = remaining < P.block_len ? remaining : P.block_len;  // decoder.rs:50
+    if (since >= 16u) { rd.block_begin(); since = 0u; }
+    rd.window(hi, lo);
+    const uint32_t ftype = hi >> 30;
+    if (ftype == 0u) {
+      const uint32_t nb = ((hi >> 26) & 15u) + 1u;  // decoder.rs:211
+      rd.advance(6);
+      if (nb <= 5u) return kDecRetryExact;          // FrameDecodeInvalidBPF: the exact path reports it
+      const int32_t half = 1 << (nb - 1u), full = 1 << nb;
+      // as many fields as fit the 32 bits one reader step may consume (2 .. 5), then one step
+      uint32_t i = 0;
+      while (i < bl) {
+        if (since >= 16u) { rd.block_begin(); since = 0u; }
+        rd.window(hi, lo);
+        uint32_t cum = 0;
+        do {
+          int32_t v = (int32_t)(funnel_l(lo, hi, cum) >> (32u - nb));
+          if (nb == 16u) {
+            lw = (int32_t)(int16_t)v;                // literal block: raw samples
+          } else {
+            if (v > half) v -= full;                 // unsigned_to_i16: strictly greater, decoder.rs:203
+            lw = (int32_t)(int16_t)(lw + v);
+          }
+          X3_GEN_EMIT(lw)
+          cum += nb;
+          i++;
+          since++;
+        } while (i < bl && cum + nb <= 32u);
+        rd.advance(cum);
+      }
+    } else {
+      rd.advance(2);
+      const uint32_t code = P.codes[ftype - 1u];
+      const int32_t inv_len = (int32_t)rice_inv_len(code);
+      const uint32_t nbk = ftype == 1u ? 1u : (ftype == 2u ? 2u : 4u);   // decoder.rs:158,180
+      const int32_t level = 1 << code;
+      // as many codes as fit the 32 bits one reader step may consume, then one step
+      uint32_t i = 0;
+      while (i < bl) {
+        if (since >= 16u) { rd.block_begin(); since = 0u; }
+        rd.window(hi, lo);
+        uint32_t cum = 0;
+        do {
+          const uint32_t t = funnel_l(lo, hi, cum);
+          const uint32_t z = clz32(t);
+          const uint32_t nbits = z + nbk;
+          if (nbits > 32u) return kDecRetryExact;    // the zero run (or the bits after it) leave the 32 bits in sight
+          if (cum + nbits > 32u) break;              // next step (never the first code of a step: cum = 0 fits)
+          const uint32_t r = (t << z) >> (32u - nbk);
+          const int32_t iv = ftype == 1u ? (int32_t)z : (int32_t)r + level * ((int32_t)z - 1);
+          if (iv < 0 || iv >= inv_len) return kDecRetryExact;   // OutOfBoundsInverse: the exact path reports it
+          lw = (int32_t)(int16_t)(lw + unfold((uint32_t)iv));
+          X3_GEN_EMIT(lw)
+          cum += nbits;
+          i++;
+          since++;
+        } while (i < bl);
+        rd.advance(cum);
+      }
+    }
+    remaining -= bl;
+  }
+  if (have_held) out[p - 1] = (int16_t)held;
+#undef X3_GEN_EMIT
+  if (rd.bits_used() > 8u * payload_len) return kDecRetryExact;
+  return kDecOk;
+}
+
 }  // namespace x3

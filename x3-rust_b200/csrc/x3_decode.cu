@@ -27,7 +27,7 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // 1. frame index
 // ------------------------------------------------------------------------------------------------
-constexpr int kScanCap = 1024;                // candidates per 128 KiB tile before falling back
+constexpr int kScanCap = 1024;                // candidates per tile (128 KiB, or 16 KiB on the retry) before falling back
 constexpr int kCountShift = 38;               // look-back value = (frames << 38) | samples
 
 struct Cand {
@@ -100,8 +100,8 @@ __global__ void __launch_bounds__(kScanThreads) scan_headers_kernel(const ScanAr
     __syncthreads();
     const uint32_t tile = s_tile;
     if (tile >= a.n_tiles) break;
-    const unsigned long long t0 = (unsigned long long)tile * kScanTileBytes;
-    const unsigned long long t1 = t0 + kScanTileBytes < a.stream_len ? t0 + kScanTileBytes : a.stream_len;
+    const unsigned long long t0 = (unsigned long long)tile * a.tile_bytes;
+    const unsigned long long t1 = t0 + a.tile_bytes < a.stream_len ? t0 + a.tile_bytes : a.stream_len;
 
     // ---- candidates: halfword 'x','3' at an even offset with a valid header behind it ----
     // Whole 16-byte pieces, four independent loads in flight per thread; key hits are rare and handled out of line.
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_headers_kernel(const ScanAr
     }
     __syncthreads();
     const uint32_t cnt = s_count < (unsigned)kScanCap ? s_count : (unsigned)kScanCap;
-    if (tid == 0 && s_count > (unsigned)kScanCap) atomicOr(a.result + 2, 1ull);
+    if (tid == 0 && s_count > (unsigned)kScanCap) atomicOr(a.result + 2, 3ull);   // bit 1: a capacity, not the stream
 
     // ---- order inside the tile (rank sort; a tile holds about a dozen frames) ----
     unsigned long long tile_samples = 0;
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_headers_kernel(const ScanAr
         fr.pad = 0;
         a.recs[rec_off + r] = fr;
       } else {
-        atomicOr(a.result + 2, 1ull);
+        atomicOr(a.result + 2, 3ull);
       }
     }
   }
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(256) place_frames_kernel(const ScanArgs a) {
       FrameRec fr = a.recs[rec_off + j];
       fr.out_off += base_samples;
       if (base_count + j < a.max_frames) a.frames[base_count + j] = fr;
-      else atomicOr(a.result + 2, 1ull);
+      else atomicOr(a.result + 2, 3ull);
     }
   }
 }
@@ -251,7 +251,7 @@ __global__ void check_chain_kernel(const ScanArgs a) {
     } else if (n <= a.max_frames && a.frames[0].pos != 0) {
       atomicOr(a.result + 2, 1ull);
     }
-    if (n > a.max_frames) atomicOr(a.result + 2, 1ull);
+    if (n > a.max_frames) atomicOr(a.result + 2, 3ull);
   }
   if (n > a.max_frames) return;
   for (unsigned long long k = i; k < n; k += stride) {
@@ -502,11 +502,16 @@ __global__ void __launch_bounds__(kDecThreads, X3_DEC_MINBLOCKS) decode_frames_k
         const uint8_t *pl = a.stream + fr.pos + kFrameHeaderLen;
         int16_t *out = a.pcm + fr.out_off;
         int r = kDecRetryExact;
-        if (dflt && frame_fast_eligible(fr.samples, fr.payload_len, (uintptr_t)pl, (uintptr_t)out)) {
+        {
+          // the tuned path for Parameters::default() frames of whole 80-sample groups; every other frame (other
+          // Parameters, a stream's short last frame, an output that is not sector aligned) takes the generic fast path
           RingReader rd;
           rd.one = a.one;
           rd.start(pl, stream_end, s_ring + tid * kRingWords);
-          r = decode_frame_fast(rd, fr.payload_len, out, fr.samples, s_stage + tid, (uint32_t)kDecThreads, s_inv, s_par);
+          if (dflt && frame_fast_eligible(fr.samples, fr.payload_len, (uintptr_t)pl, (uintptr_t)out))
+            r = decode_frame_fast(rd, fr.payload_len, out, fr.samples, s_stage + tid, (uint32_t)kDecThreads, s_inv, s_par);
+          else
+            r = decode_frame_generic(rd, fr.payload_len, out, fr.samples, a.P);
           cp_async_wait_all();
         }
         if (r == kDecRetryExact) r = decode_frame_exact(pl, fr.payload_len, out, fr.samples, a.P);

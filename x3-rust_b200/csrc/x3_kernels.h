@@ -85,11 +85,14 @@ struct ScanArgs {
   FrameRec *recs;                   // [max_frames] the tiles' records in arrival order (sample offsets tile-relative)
   unsigned long long *rec_cursor;   // zeroed
   unsigned int *ticket;             // zeroed
-  unsigned long long *result;       // [0] n_frames, [1] total samples, [2] flags (1 = needs host walk)
+  unsigned long long *result;       // [0] n_frames, [1] total samples, [2] flags (bit 0: the table is not proven, needs
+                                    // the host walk or a retry; bit 1: because a capacity -- candidates per tile, table size -- was exceeded)
   const uint16_t *crc_tables;
   uint32_t n_tiles;
+  uint32_t tile_bytes;              // kScanTileBytes, or kScanTileBytesSmall on the retry (multiple of 16)
 };
 constexpr uint32_t kScanTileBytes = 128 * 1024;
+constexpr uint32_t kScanTileBytesSmall = 16 * 1024;   // >= 22 bytes per frame: at most 745 frames per tile, under the cap
 cudaError_t launch_scan(const ScanArgs &a, cudaStream_t stream);
 cudaError_t launch_chain_check(const ScanArgs &a, cudaStream_t stream);
 

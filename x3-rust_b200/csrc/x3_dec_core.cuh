@@ -504,12 +504,10 @@ X3_HD int decode_frame_generic(Reader &rd, uint32_t payload_len, int16_t *out, u
   }
   X3_GEN_EMIT(lw)
   uint32_t remaining = samples - 1u;
-  // The reader is topped up every 16 to 32 samples (<= 66 bytes of payload), never twice in a row: a top-up waits for
-  // the copies of the one before it, so two in quick succession would wait out a whole memory round trip.
-  uint32_t since = 16u;
+  // the reader is topped up at every block start and every <= 16 samples inside a block (<= 34 bytes of payload)
   while (remaining > 0u) {
     const uint32_t bl = remaining < P.block_len ? remaining : P.block_len;  // decoder.rs:50
-    if (since >= 16u) { rd.block_begin(); since = 0u; }
+    rd.block_begin();
     rd.window(hi, lo);
     const uint32_t ftype = hi >> 30;
     if (ftype == 0u) {
@@ -520,7 +518,7 @@ X3_HD int decode_frame_generic(Reader &rd, uint32_t payload_len, int16_t *out, u
       // as many fields as fit the 32 bits one reader step may consume (2 .. 5), then one step
       uint32_t i = 0;
       while (i < bl) {
-        if (since >= 16u) { rd.block_begin(); since = 0u; }
+        if ((i & 15u) >= 12u && i >= 12u) rd.block_begin();
         rd.window(hi, lo);
         uint32_t cum = 0;
         do {
@@ -534,7 +532,6 @@ X3_HD int decode_frame_generic(Reader &rd, uint32_t payload_len, int16_t *out, u
           X3_GEN_EMIT(lw)
           cum += nb;
           i++;
-          since++;
         } while (i < bl && cum + nb <= 32u);
         rd.advance(cum);
       }
@@ -547,7 +544,7 @@ X3_HD int decode_frame_generic(Reader &rd, uint32_t payload_len, int16_t *out, u
       // as many codes as fit the 32 bits one reader step may consume, then one step
       uint32_t i = 0;
       while (i < bl) {
-        if (since >= 16u) { rd.block_begin(); since = 0u; }
+        if ((i & 15u) >= 12u && i >= 12u) rd.block_begin();
         rd.window(hi, lo);
         uint32_t cum = 0;
         do {
@@ -563,7 +560,6 @@ X3_HD int decode_frame_generic(Reader &rd, uint32_t payload_len, int16_t *out, u
           X3_GEN_EMIT(lw)
           cum += nbits;
           i++;
-          since++;
         } while (i < bl);
         rd.advance(cum);
       }

@@ -825,8 +825,9 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const __grid
 //               barrier) and finishes: slices by Horner, tail, header CRC;
 //   out      -- the PREVIOUS frame's window goes to the stream now: its offset (which needs every earlier frame's size)
 //               has had a whole frame time to arrive.  16-byte stores, realigned with PRMT (offsets are only even).
-// Frames that are not regular -- a payload larger than a window (8 KiB; literal / BFP heavy frames), a strip of less
-// than 32 bits (tiny frames) -- take slow_frame(): merging relocation in rounds, written out at once.
+// A payload of 8 .. 16 KiB (BFP / literal heavy frames) takes both windows as one buffer, after the pending frame has
+// gone out; only a payload larger than that (literal almost throughout) takes slow_frame(): merging relocation in
+// rounds, written out at once, which needs the frame's own offset.
 // ------------------------------------------------------------------------------------------------
 constexpr int NTS = kEncStripThreads;                 // 128
 constexpr uint32_t kWinBytes = 8192;                  // multiple of 1024 (32 chunks of 32 bytes)
@@ -1016,15 +1017,17 @@ constexpr int kMiscT = 64, kMiscWords = 192;
 // The frame waiting in a window: every thread keeps its description in registers (the values are uniform); only the
 // two CRCs, which warp 0 produces late, travel through shared memory (misc[24 + q]).
 struct PendingFrame {
-  uint32_t q;            // window (2 = nothing pending)
+  uint32_t q;            // window 0 or 1; 2 = nothing pending; 3 = both windows as one buffer (a payload of 8 .. 16 KiB)
   uint32_t f, n, len;    // frame index, samples, payload bytes
 };
+constexpr uint32_t kBothBytes = 2u * kWinBytes;   // the two windows and the slack between them are contiguous
+__device__ __forceinline__ uint32_t *window_of(const StripShared &S, uint32_t q) { return q == 3u ? S.win : S.win + q * kWinStride; }
 // the pending frame goes to the stream; its offset is in misc[10..13).  All threads.
 __device__ __forceinline__ void flush_pending(const EncodeArgs &a, const StripShared &S, const PendingFrame &p, int tid,
                                               const uint32_t *slot, int hdr_warp = 1) {
   if (slot[2]) {
     const unsigned long long goff = (unsigned long long)slot[0] | ((unsigned long long)slot[1] << 32);
-    copy_window_out(a.out + goff + kFrameHeaderLen, S.win + p.q * kWinStride, p.len, tid);
+    copy_window_out(a.out + goff + kFrameHeaderLen, window_of(S, p.q), p.len, tid);
     if ((tid >> 5) == hdr_warp) write_header(a.out, goff, p.n, p.len, S.misc[24 + p.q], tid & 31);
   }
 }
@@ -1042,13 +1045,13 @@ __device__ __noinline__ uint32_t slow_frame(const EncodeArgs &a, const StripShar
   uint32_t *misc = S.misc;
   const uint16_t *NA = S.N + 64 * (lane & 3), *NB = S.N + 64 * ((lane >> 2) ? 3 + (lane >> 2) : 0);
   if (tid == 32) {
-    if (pend.q < 2u) wait_offset(a, pend.f, (uint32_t)kFrameHeaderLen + pend.len, misc + 10);
+    if (pend.q != 2u) wait_offset(a, pend.f, (uint32_t)kFrameHeaderLen + pend.len, misc + 10);
     wait_offset(a, f, (uint32_t)kFrameHeaderLen + payload_len, misc + 13);
     misc[8] = atomicAdd(a.ticket, 1u);
   }
+  __syncthreads();                                   // every warp is here: the previous frame's finisher is done with S.V
   if (tid < (int)kMaxSlicesStrip) S.V[tid] = 0u;
-  __syncthreads();
-  if (pend.q < 2u) flush_pending(a, S, pend, tid, misc + 10);
+  if (pend.q != 2u) flush_pending(a, S, pend, tid, misc + 10);
   const unsigned long long goff = (unsigned long long)misc[13] | ((unsigned long long)misc[14] << 32);
   const bool fits = misc[15] != 0u;
   const uint32_t f_next = misc[8];
@@ -1140,7 +1143,7 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
     // scheduler the critical path of all frames)
     const int fin = (int)(it & 3u), pol = (int)((it + 1u) & 3u);
     unsigned long long pend_status = 0;
-    if (wid == pol && lane == 0 && pend.q < 2u) pend_status = ld_status(a.status + pend.f);
+    if (wid == pol && lane == 0 && pend.q != 2u) pend_status = ld_status(a.status + pend.f);
     cp_async_wait_all();
     __syncwarp();                                      // this warp's rows are staged (nobody else touches them)
 
@@ -1178,7 +1181,7 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
     }
     if (lane == 31) s_misc[wid] = incl;
     s_misc[kMiscT + tid] = T;
-    uint32_t *s_V = S.V + par * kMaxSlicesStrip;
+    uint32_t *s_V = S.V + (it & 1u) * kMaxSlicesStrip;   // by iteration: the finisher of the previous frame may still read the other one
     if (tid >= 32 && tid < 32 + (int)kMaxSlicesStrip) s_V[tid - 32] = 0u;
     uint32_t wbase = 0;
     if (wid == 0) {
@@ -1210,18 +1213,19 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
       const uint32_t pl = payload_bytes(tb);
       st_status(a.status + f, kFlagAgg | (unsigned long long)((uint32_t)kFrameHeaderLen + pl));
       s_misc[4 + (it & 1u)] = tb;
-      if (pl <= kWinBytes) ticket = atomicAdd(a.ticket, 1u);
+      if (pl <= kBothBytes) ticket = atomicAdd(a.ticket, 1u);
     }
     // the pending frame's offset (published a frame time ago): one thread asks, everybody knows after (B4)
     uint32_t *off_slot = s_misc + 32 + 4 * (it & 1u);
-    if (wid == pol && lane == 0 && pend.q < 2u)
+    if (wid == pol && lane == 0 && pend.q != 2u)
       wait_offset(a, pend.f, (uint32_t)kFrameHeaderLen + pend.len, off_slot, pend_status);
     // The window about to be written is the one the previous iteration copied out at its end: every warp has said
     // "my share is out" on an mbarrier since (a split barrier: the arrival was a whole pack phase ago, so nobody waits).
     if (it) mbar_wait(mb_flush, (it - 1u) & 1u);
     // relocation, before the frame is known to fit the window: a strip that would leave it stays where it is (the
     // frame then takes the slow path, which starts over from the rows)
-    if ((uint32_t)tid < nstrips && ((O + T + 31u) >> 5) <= kWinWords)
+    const bool optimistic = pend.q != 3u;              // a pending frame that fills both windows must go out first
+    if (optimistic && (uint32_t)tid < nstrips && ((O + T + 31u) >> 5) <= kWinWords)
       strip_relocate_fast(row, T, O, tid ? s_misc[kMiscT + tid - 1] : 32u, (uint32_t)tid + 1u == nstrips, win);
     if (tid == NTS - 1) s_misc[6 + (it & 1u)] = ticket;
     __syncthreads();                                   // (B4) window complete; size, ticket and pending offset visible
@@ -1229,7 +1233,7 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
     const uint32_t payload_len = payload_bytes(total_bits);
     const uint32_t nch = payload_len >> 5;             // whole 32-byte CRC chunks
 
-    if (payload_len <= kWinBytes) {
+    if (payload_len <= kWinBytes && optimistic) {
       const uint32_t f_next = s_misc[6 + (it & 1u)];
       if (f_next < a.n_frames)
         stage_rows(a.pcm + (unsigned long long)f_next * spf, f_next == last_f ? last_n : spf, S.rows, S.next, wid, lane);
@@ -1240,9 +1244,34 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
       } else {
         asm volatile("bar.arrive 1, 128;\n" ::: "memory");
       }
-      if (pend.q < 2u) flush_pending(a, S, pend, tid, off_slot, pol);
+      if (pend.q != 2u) flush_pending(a, S, pend, tid, off_slot, pol);
       pend.q = par; pend.f = f; pend.n = n; pend.len = payload_len;
       par ^= 1u;
+      f = f_next;
+    } else if (payload_len <= kBothBytes) {
+      // A payload of 8 .. 16 KiB (BFP / literal heavy frames), or any frame behind one: the pending frame goes out
+      // FIRST (its offset has had a frame time to arrive), then the strips are relocated into the window, or into
+      // both windows taken as one buffer.  Two more CTA barriers than the common path, but still no wait for the
+      // frame's own offset.
+      if (pend.q != 2u) flush_pending(a, S, pend, tid, off_slot, pol);
+      __syncthreads();
+      const uint32_t q = payload_len <= kWinBytes ? par : 3u;
+      uint32_t *wq = window_of(S, q);
+      if ((uint32_t)tid < nstrips)
+        strip_relocate_fast(row, T, O, tid ? s_misc[kMiscT + tid - 1] : 32u, (uint32_t)tid + 1u == nstrips, wq);
+      __syncthreads();
+      const uint32_t f_next = s_misc[6 + (it & 1u)];
+      if (f_next < a.n_frames)
+        stage_rows(a.pcm + (unsigned long long)f_next * spf, f_next == last_f ? last_n : spf, S.rows, S.next, wid, lane);
+      crc_slices(wq, 0u, nch, nch, s_V, s_T2, s_N, NA, NB, wid, lane);
+      if (wid == fin) {
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        if (lane == 0) s_misc[24 + q] = crc_finish(s_V, wq, 32u * nch, payload_len, n, s_T2, s_N);
+      } else {
+        asm volatile("bar.arrive 1, 128;\n" ::: "memory");
+      }
+      pend.q = q; pend.f = f; pend.n = n; pend.len = payload_len;
+      if (q != 3u) par ^= 1u;
       f = f_next;
     } else {
       f = slow_frame(a, S, f, n, T, O, total_bits, pend, spf, last_f, last_n);
@@ -1262,7 +1291,7 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
   }
   // ---- drain: the last frame of this CTA is still in its window ----
   __syncthreads();
-  if (pend.q < 2u) {
+  if (pend.q != 2u) {
     if (tid == 32) wait_offset(a, pend.f, (uint32_t)kFrameHeaderLen + pend.len, s_misc + 10);
     __syncthreads();
     flush_pending(a, S, pend, tid, s_misc + 10);

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define X3_B200_ABI_VERSION 1
+#define X3_B200_ABI_VERSION 2
 
 /* ---- error codes ------------------------------------------------------------------------- */
 enum {
@@ -95,6 +95,9 @@ int x3_params_validate(const x3_params *p);
 /* Upper bound on the bytes encoder::encode writes for n samples; the reference offers none
  * (README.md:46-47 suggests n*2, which is too small for incompressible input). */
 size_t x3_encode_bound(size_t n_samples, const x3_params *p);
+/* The same for encoder::encode_frame (encoder.rs:175): ONE frame holding all n_samples (<= 65535), whatever
+ * blocks_per_frame says.  0 for parameters x3_params_validate rejects. */
+size_t x3_encode_frame_bound(size_t n_samples, const x3_params *p);
 const char *x3_strerror(int code);
 const char *x3_last_cuda_error(void);
 
@@ -130,9 +133,28 @@ int x3_decode_host(const uint8_t *frames, size_t len, const x3_params *p, int16_
                    size_t pcm_cap, size_t *n_out, x3_decode_result *res);
 int x3_decode_device(const uint8_t *d_frames, size_t len, const x3_params *p, int16_t *d_pcm,
                      size_t pcm_cap, size_t *n_out, x3_decode_result *res, void *cuda_stream);
-/* decoder::decode_frame (decoder.rs:36-58): one payload (no header), `samples` from its header. */
+/* decoder::decode_frame (decoder.rs:36-58): one payload (no header), `samples` from its header.  Like the
+ * reference's function it has no 24 KiB payload limit (that one belongs to X3aReader, decodefile.rs:118-121):
+ * any payload below Frame::MAX_LENGTH is taken. */
 int x3_decode_frame_host(const uint8_t *payload, size_t payload_len, const x3_params *p,
                          int16_t *pcm, size_t pcm_cap, size_t samples, size_t *n_out);
+
+/* ---- frame-range sharding across GPUs ----------------------------- */
+/* Frames are independent (own first sample, own CRCs, even length: encoder.rs:175-214), so a recording is cut at
+ * frame boundaries, every rank encodes / decodes its own range with the *_device calls above, and the only thing
+ * ranks exchange is the compressed size of their shard (one NCCL / MPI all-gather of a uint64, done by the host
+ * program).  These helpers are the arithmetic around that exchange; none of them needs a GPU except the copy.
+ *
+ * Sample range [*s0, *s1) of rank's shard of an n_samples recording: frames [rank*F/world, (rank+1)*F/world). */
+int x3_shard_range(uint64_t n_samples, const x3_params *p, uint32_t rank, uint32_t world, uint64_t *s0, uint64_t *s1);
+/* Whole files dealt by cumulative frame count (a file keeps its own archive header, so files are never split):
+ * rank_of_file[i] = the rank that takes file i. */
+int x3_deal_files(const uint64_t *frames_per_file, size_t n_files, uint32_t world, uint32_t *rank_of_file);
+/* Byte offset of rank's shard in the concatenated stream, from the all-gathered shard sizes. */
+int x3_shard_base(const uint64_t *shard_bytes, uint32_t world, uint32_t rank, uint64_t *base);
+/* Optional gather: copy a shard's frame bytes to d_stream + base, where d_stream may live on another GPU of the box
+ * (peer copy over NVLink; unified addressing picks the route).  Stream-ordered on cuda_stream, no synchronisation. */
+int x3_place_shard_device(uint8_t *d_stream, uint64_t base, const uint8_t *d_shard, size_t shard_bytes, void *cuda_stream);
 
 /* ---- synthetic signals (bench / tests) ---------------------------- */
 /* Fill d_out[0..count) on the device with samples n0..n0+count-1 of generator `kind`

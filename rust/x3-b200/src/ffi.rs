@@ -40,6 +40,7 @@ extern "C" {
     pub fn x3_params_default(p: *mut x3_params) -> c_int;
     pub fn x3_params_validate(p: *const x3_params) -> c_int;
     pub fn x3_encode_bound(n_samples: usize, p: *const x3_params) -> usize;
+    pub fn x3_encode_frame_bound(n_samples: usize, p: *const x3_params) -> usize;
     pub fn x3_strerror(code: c_int) -> *const c_char;
     pub fn x3_last_cuda_error() -> *const c_char;
     pub fn x3_write_frame_header(num_samples: usize, id: u8, payload_len: usize, payload_crc: u16, header: *mut u8) -> c_int;
@@ -57,4 +58,12 @@ extern "C" {
                             n_out: *mut usize, res: *mut x3_decode_result, stream: *mut c_void) -> c_int;
     pub fn x3_decode_frame_host(payload: *const u8, len: usize, p: *const x3_params, pcm: *mut i16, cap: usize,
                                 samples: usize, n_out: *mut usize) -> c_int;
+    // frame-range sharding across GPUs (one process per GPU; the size all-gather is the host program's)
+    pub fn x3_shard_range(n_samples: u64, p: *const x3_params, rank: u32, world: u32, s0: *mut u64, s1: *mut u64) -> c_int;
+    pub fn x3_deal_files(frames_per_file: *const u64, n_files: usize, world: u32, rank_of_file: *mut u32) -> c_int;
+    pub fn x3_shard_base(shard_bytes: *const u64, world: u32, rank: u32, base: *mut u64) -> c_int;
+    pub fn x3_place_shard_device(d_stream: *mut u8, base: u64, d_shard: *const u8, shard_bytes: usize, stream: *mut c_void) -> c_int;
+    pub fn x3_synth_device(kind: c_int, seed: u32, fs: u32, n0: u64, count: u64, d_out: *mut i16, stream: *mut c_void) -> c_int;
+    pub fn x3_kernel_launch_count() -> u64;
+    pub fn x3_last_kernel_ms(ms: *mut f32) -> c_int;
 }

@@ -5,30 +5,76 @@ pub mod ffi;
 pub mod x3;
 
 pub mod bytewriter {
-    //! src/bytewriter.rs: the subset the GPU path needs (frame sizes are known before writing, so no seek)
+    //! src/bytewriter.rs: the trait is the reference's, item for item (bytewriter.rs:14-22), so that a caller's own
+    //! `ByteWriter` plugs in unchanged: `align<const N>`, `write_all(impl AsRef<[u8]>)`, `flush`, `seek`,
+    //! `stream_position`.  The GPU path knows every frame's size before it writes, so it never seeks itself; `seek` is
+    //! there for callers (and for the trait to be the same).
     use crate::error::{Result, X3Error};
+    #[cfg(feature = "std")]
+    pub use std::io::SeekFrom;
+    #[cfg(not(feature = "std"))]
+    pub enum SeekFrom { Start(u64), End(i64), Current(i64) }
+
     pub trait ByteWriter {
-        fn align2(&mut self) -> Result<()>;
-        fn write_all(&mut self, value: &[u8]) -> Result<()>;
+        fn align<const N: usize>(&mut self) -> Result<usize>;
+        fn write_all(&mut self, value: impl AsRef<[u8]>) -> Result<()>;
+        fn flush(&mut self) -> Result<()>;
+        fn seek(&mut self, pos: SeekFrom) -> Result<u64>;
         fn stream_position(&mut self) -> Result<u64>;
     }
-    pub struct SliceByteWriter<'a> { slice: &'a mut [u8], p_byte: usize }
-    impl<'a> SliceByteWriter<'a> { pub fn new(slice: &'a mut [u8]) -> Self { SliceByteWriter { slice, p_byte: 0 } } }
+
+    /// A caller-owned slice; never grows (ByteWriterInsufficientMemory, bytewriter.rs:72-74,88-90).
+    pub struct SliceByteWriter<'a> { slice: &'a mut [u8], at: usize, high_water: usize }
+    impl<'a> SliceByteWriter<'a> {
+        pub fn new(slice: &'a mut [u8]) -> Self { SliceByteWriter { slice, at: 0, high_water: 0 } }
+    }
     impl<'a> ByteWriter for SliceByteWriter<'a> {
-        fn align2(&mut self) -> Result<()> { if self.p_byte % 2 == 1 { self.write_all(&[0u8]) } else { Ok(()) } }
-        fn write_all(&mut self, v: &[u8]) -> Result<()> {
-            if v.len() > self.slice.len() - self.p_byte { return Err(X3Error::ByteWriterInsufficientMemory); }
-            self.slice[self.p_byte..self.p_byte + v.len()].copy_from_slice(v);
-            self.p_byte += v.len();
+        fn align<const N: usize>(&mut self) -> Result<usize> {
+            let pad = (N - self.at % N) % N;
+            if pad > 0 { self.write_all(&[0u8; N][..pad])?; }
+            Ok(pad)
+        }
+        fn write_all(&mut self, value: impl AsRef<[u8]>) -> Result<()> {
+            let v = value.as_ref();
+            let end = self.at.checked_add(v.len()).ok_or(X3Error::ByteWriterInsufficientMemory)?;
+            if end > self.slice.len() { return Err(X3Error::ByteWriterInsufficientMemory); }
+            self.slice[self.at..end].copy_from_slice(v);
+            self.at = end;
+            if end > self.high_water { self.high_water = end; }
             Ok(())
         }
-        fn stream_position(&mut self) -> Result<u64> { Ok(self.p_byte as u64) }
+        fn flush(&mut self) -> Result<()> { Ok(()) }
+        fn seek(&mut self, pos: SeekFrom) -> Result<u64> {
+            let target: i128 = match pos {
+                SeekFrom::Start(p) => p as i128,
+                SeekFrom::End(d) => self.high_water as i128 + d as i128,
+                SeekFrom::Current(d) => self.at as i128 + d as i128,
+            };
+            if target < 0 || target > self.slice.len() as i128 { return Err(X3Error::ByteWriterInsufficientMemory); }
+            self.at = target as usize;
+            if self.at > self.high_water { self.high_water = self.at; }
+            Ok(self.at as u64)
+        }
+        fn stream_position(&mut self) -> Result<u64> { Ok(self.at as u64) }
     }
+
+    /// Any `Write + Seek` (a file behind a BufWriter in wav_to_x3a).
+    #[cfg(feature = "std")]
     pub struct StreamByteWriter<'a, W: std::io::Write + std::io::Seek> { writer: &'a mut W }
-    impl<'a, W: std::io::Write + std::io::Seek> StreamByteWriter<'a, W> { pub fn new(writer: &'a mut W) -> Self { StreamByteWriter { writer } } }
+    #[cfg(feature = "std")]
+    impl<'a, W: std::io::Write + std::io::Seek> StreamByteWriter<'a, W> {
+        pub fn new(writer: &'a mut W) -> Self { StreamByteWriter { writer } }
+    }
+    #[cfg(feature = "std")]
     impl<'a, W: std::io::Write + std::io::Seek> ByteWriter for StreamByteWriter<'a, W> {
-        fn align2(&mut self) -> Result<()> { if self.writer.stream_position()? % 2 == 1 { self.write_all(&[0u8]) } else { Ok(()) } }
-        fn write_all(&mut self, v: &[u8]) -> Result<()> { Ok(self.writer.write_all(v)?) }
+        fn align<const N: usize>(&mut self) -> Result<usize> {
+            let pad = (N - (self.writer.stream_position()? as usize) % N) % N;
+            if pad > 0 { self.write_all(&[0u8; N][..pad])?; }
+            Ok(pad)
+        }
+        fn write_all(&mut self, value: impl AsRef<[u8]>) -> Result<()> { Ok(std::io::Write::write_all(self.writer, value.as_ref())?) }
+        fn flush(&mut self) -> Result<()> { Ok(self.writer.flush()?) }
+        fn seek(&mut self, pos: SeekFrom) -> Result<u64> { Ok(self.writer.seek(pos)?) }
         fn stream_position(&mut self) -> Result<u64> { Ok(self.writer.stream_position()?) }
     }
 }
@@ -66,7 +112,7 @@ pub mod encoder {
     pub fn encode_channel<W: ByteWriter>(ch: &x3::Channel, writer: &mut W) -> Result<()> {
         let mut stats = [0usize; 6];
         if !ch.wav.is_empty() {
-            writer.align2()?;  // encoder.rs:182
+            writer.align::<2>()?;  // encoder.rs:182
             let data = encode_slice(ch.wav, &ch.params, &mut stats)?;
             writer.write_all(&data)?;
         }
@@ -76,10 +122,10 @@ pub mod encoder {
     /// encoder::encode_frame (encoder.rs:175)
     pub fn encode_frame<W: ByteWriter>(wav: &[i16], writer: &mut W, params: &x3::Parameters, stats: &mut [usize; 6]) -> Result<()> {
         let p = params.c_struct();
-        let cap = 24 + 2 * wav.len() + wav.len() / 4 + 64;
+        let cap = unsafe { ffi::x3_encode_frame_bound(wav.len(), &p) }.max(32);   // 2.75 bytes per sample at block_len 1
         let mut out = vec![0u8; cap];
         let (mut len, mut st) = (0usize, ffi::x3_stats::default());
-        writer.align2()?;
+        writer.align::<2>()?;
         check(unsafe { ffi::x3_encode_frame_host(wav.as_ptr(), wav.len(), &p, out.as_mut_ptr(), cap, &mut len, &mut st) })?;
         for k in 0..6 { stats[k] += st.samples_by_mode[k] as usize; }
         writer.write_all(&out[..len])
@@ -180,12 +226,23 @@ pub mod decodefile {
         if d.len() < 28 { return Err(X3Error::Io(std::io::ErrorKind::UnexpectedEof.into())); }
         if &d[..8] != x3::Archive::ID { return Err(X3Error::ArchiveHeaderXMLInvalidKey); }
         let h = decoder::read_frame_header(&d[8..28])?;
+        // a truncated archive header is an Io error in the reference (read_exact, decodefile.rs:163-166), not a panic
+        if d.len() < 28 + h.payload_len { return Err(X3Error::Io(std::io::ErrorKind::UnexpectedEof.into())); }
         let (fs, params) = parse_xml(&String::from_utf8_lossy(&d[28..28 + h.payload_len]))?;
         let frames = &d[28 + h.payload_len..];
+        // samples of the whole frames (the decode itself stops where the reference would: decodefile.rs:107-116).
+        // `pos + 20 < len`, not `len - pos > 20`: a truncated last frame leaves pos beyond the end.
         let mut total = 0usize;
         let mut pos = 0usize;
-        while frames.len() - pos > 20 {
-            match decoder::read_frame_header(&frames[pos..pos + 20]) { Ok(fh) => { total += fh.samples as usize; pos += 20 + fh.payload_len; } Err(_) => break }
+        while pos + 20 < frames.len() {
+            match decoder::read_frame_header(&frames[pos..pos + 20]) {
+                Ok(fh) => {
+                    if pos + 20 + fh.payload_len > frames.len() { break; }   // truncated: the reference ends cleanly here
+                    total += fh.samples as usize;
+                    pos += 20 + fh.payload_len;
+                }
+                Err(_) => break,
+            }
         }
         let mut pcm = vec![0i16; total.max(1)];
         let (rc, _res, n) = decoder::decode_stream(frames, &params, &mut pcm[..total]);

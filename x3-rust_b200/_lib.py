@@ -35,6 +35,11 @@ SYMBOLS = {
     "x3_params_default": (C.c_int, [_P(x3_params)]),
     "x3_params_validate": (C.c_int, [_P(x3_params)]),
     "x3_encode_bound": (C.c_size_t, [C.c_size_t, _P(x3_params)]),
+    "x3_encode_frame_bound": (C.c_size_t, [C.c_size_t, _P(x3_params)]),
+    "x3_shard_range": (C.c_int, [C.c_uint64, _P(x3_params), C.c_uint32, C.c_uint32, _P(C.c_uint64), _P(C.c_uint64)]),
+    "x3_deal_files": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p]),
+    "x3_shard_base": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _P(C.c_uint64)]),
+    "x3_place_shard_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_size_t, C.c_void_p]),
     "x3_strerror": (C.c_char_p, [C.c_int]),
     "x3_last_cuda_error": (C.c_char_p, []),
     "x3_write_frame_header": (C.c_int, [C.c_size_t, C.c_uint8, C.c_size_t, C.c_uint16, C.c_void_p]),

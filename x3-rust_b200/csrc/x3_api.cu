@@ -23,6 +23,7 @@ namespace {
 std::atomic<uint64_t> g_launches{0};
 thread_local char tl_cuda_err[256] = "";
 thread_local float tl_ms[4] = {0.f, 0.f, 0.f, 0.f};
+thread_local uint32_t tl_max_payload = x3::kReadBufferSize;   // x3_decode_frame_host lifts the stream reader's limit
 
 int cuda_fail(cudaError_t e, const char *what) {
   snprintf(tl_cuda_err, sizeof tl_cuda_err, "%s: %s", what, cudaGetErrorString(e));
@@ -192,7 +193,9 @@ uint32_t max_block_bits_of(const x3_params *p) {
   return a > b ? a : b;
 }
 
+thread_local bool tl_one_frame = false;   // set by the encode_frame entry points: the frame is the whole input
 int derive(const x3_params *p, Derived *d) {
+  const bool one_frame = tl_one_frame;
   if (!p) return X3_ERR_INVALID_ARGUMENT;
   if (p->block_len == 0 || p->blocks_per_frame == 0) return X3_ERR_INVALID_ARGUMENT;
   for (int k = 0; k < 3; k++)
@@ -202,7 +205,8 @@ int derive(const x3_params *p, Derived *d) {
   if (p->block_len > (uint32_t)kMaxBlockLen) return X3_ERR_UNSUPPORTED_PARAMS;  // reference panics (wav_diff[60])
   if (p->thresholds[2] > 4096u) return X3_ERR_UNSUPPORTED_PARAMS;
   const unsigned long long spf = (unsigned long long)p->block_len * p->blocks_per_frame;
-  if (spf > 65535ull) return X3_ERR_UNSUPPORTED_PARAMS;  // header field is u16 (encoder.rs:141)
+  // header field is u16 (encoder.rs:141); a single frame may round its block count up past it, its sample count cannot
+  if (spf > 65535ull + (one_frame ? p->block_len - 1u : 0u)) return X3_ERR_UNSUPPORTED_PARAMS;
   d->P.block_len = p->block_len;
   d->P.spf = (uint32_t)spf;
   for (int k = 0; k < 3; k++) { d->P.codes[k] = p->codes[k]; d->P.thresholds[k] = p->thresholds[k]; }
@@ -608,10 +612,65 @@ int x3_encode_frame_host(const int16_t *pcm, size_t n_samples, const x3_params *
   // one frame = encode() with a frame length that covers the whole input
   x3_params q = *p;
   if (q.block_len == 0) return X3_ERR_INVALID_ARGUMENT;
+  q.blocks_per_frame = (uint32_t)((n_samples + q.block_len - 1) / q.block_len);   // may round up past 65535 samples
+  tl_one_frame = true;
+  const int rc = x3_encode_host(pcm, n_samples, &q, out, out_cap, out_len, stats);
+  tl_one_frame = false;
+  return rc;
+}
+
+size_t x3_encode_frame_bound(size_t n_samples, const x3_params *p) {
+  if (!p || p->block_len == 0 || n_samples == 0 || n_samples > 65535) return 0;
+  x3_params q = *p;
   q.blocks_per_frame = (uint32_t)((n_samples + q.block_len - 1) / q.block_len);
-  if ((unsigned long long)q.blocks_per_frame * q.block_len > 65535ull) q.blocks_per_frame = 65535u / q.block_len;
-  if ((unsigned long long)q.blocks_per_frame * q.block_len < n_samples) return X3_ERR_UNSUPPORTED_PARAMS;
-  return x3_encode_host(pcm, n_samples, &q, out, out_cap, out_len, stats);
+  tl_one_frame = true;
+  const size_t b = x3_encode_bound(n_samples, &q);
+  tl_one_frame = false;
+  return b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// frame-range sharding helpers (no GPU needed except the copy)
+// ------------------------------------------------------------------------------------------------
+int x3_shard_range(uint64_t n_samples, const x3_params *p, uint32_t rank, uint32_t world, uint64_t *s0, uint64_t *s1) {
+  if (!p || !s0 || !s1 || world == 0 || rank >= world) return X3_ERR_INVALID_ARGUMENT;
+  const uint64_t spf = (uint64_t)p->block_len * p->blocks_per_frame;
+  if (spf == 0) return X3_ERR_INVALID_ARGUMENT;
+  const uint64_t frames = (n_samples + spf - 1) / spf;
+  const unsigned __int128 f0 = (unsigned __int128)frames * rank / world, f1 = (unsigned __int128)frames * (rank + 1u) / world;
+  const uint64_t a = (uint64_t)f0 * spf, b = (uint64_t)f1 * spf;
+  *s0 = a < n_samples ? a : n_samples;
+  *s1 = b < n_samples ? b : n_samples;
+  return X3_OK;
+}
+
+int x3_deal_files(const uint64_t *frames_per_file, size_t n_files, uint32_t world, uint32_t *rank_of_file) {
+  if ((!frames_per_file || !rank_of_file) && n_files) return X3_ERR_INVALID_ARGUMENT;
+  if (world == 0) return X3_ERR_INVALID_ARGUMENT;
+  unsigned __int128 total = 0, acc = 0;
+  for (size_t i = 0; i < n_files; i++) total += frames_per_file[i];
+  for (size_t i = 0; i < n_files; i++) {
+    uint64_t r = total ? (uint64_t)(acc * world / total) : 0;   // the rank whose equal share holds the file's first frame
+    if (r > world - 1u) r = world - 1u;
+    rank_of_file[i] = (uint32_t)r;
+    acc += frames_per_file[i];
+  }
+  return X3_OK;
+}
+
+int x3_shard_base(const uint64_t *shard_bytes, uint32_t world, uint32_t rank, uint64_t *base) {
+  if (!shard_bytes || !base || rank >= world) return X3_ERR_INVALID_ARGUMENT;
+  uint64_t b = 0;
+  for (uint32_t r = 0; r < rank; r++) b += shard_bytes[r];
+  *base = b;
+  return X3_OK;
+}
+
+int x3_place_shard_device(uint8_t *d_stream, uint64_t base, const uint8_t *d_shard, size_t shard_bytes, void *cuda_stream) {
+  if ((!d_stream || !d_shard) && shard_bytes) return X3_ERR_INVALID_ARGUMENT;
+  if (shard_bytes == 0) return X3_OK;
+  CU(cudaMemcpyAsync(d_stream + base, d_shard, shard_bytes, cudaMemcpyDefault, (cudaStream_t)cuda_stream));
+  return X3_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -643,7 +702,7 @@ int host_walk(const uint8_t *s, size_t len, std::vector<FrameRec> &frames, unsig
     frames.push_back(fr);
     samples += h.samples;
     *total_samples = samples;
-    if (h.payload_len > kReadBufferSize) return X3_OK;  // the frame itself reports InvalidPayloadLen (crc kernel)
+    if (h.payload_len > tl_max_payload) return X3_OK;  // the frame itself reports InvalidPayloadLen (crc kernel)
     remaining -= h.payload_len;
     cursor += h.payload_len;
   }
@@ -750,6 +809,7 @@ int decode_device_attempt(const uint8_t *d_frames, size_t len, const x3_params *
   da.frame_status = reinterpret_cast<int *>(ws + o_fstat);
   da.crc_status = reinterpret_cast<int *>(ws + o_cstat);
   da.one = 1u;
+  da.max_payload = tl_max_payload;
   da.result = reinterpret_cast<unsigned long long *>(ws + o_dres);
   da.crc_tables = ds->crc_dev;
 
@@ -1063,7 +1123,9 @@ int x3_decode_frame_host(const uint8_t *payload, size_t payload_len, const x3_pa
   x3_write_frame_header(samples, 1, payload_len, x3_crc16(payload, payload_len), buf.data());
   memcpy(buf.data() + 20, payload, payload_len);
   x3_decode_result r;
+  tl_max_payload = kFrameMaxLength;   // decoder::decode_frame has no X3_READ_BUFFER_SIZE limit (that is X3aReader's)
   int rc = x3_decode_host(buf.data(), buf.size(), p, pcm, pcm_cap, n_out, &r);
+  tl_max_payload = kReadBufferSize;
   if (rc == X3_OK && r.frame_errors) return r.first_bad_code;  // decode_frame itself returns the Err
   return rc;
 }

@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(X3_CRC_THREADS) crc_frames_kernel(const Decode
     const unsigned long long pend = fr.pos + kFrameHeaderLen + fr.payload_len;
     if (pend > a.stream_len) {
       status = kDecErrPanic;  // never produced by the index (truncated frames are dropped); defensive
-    } else if (fr.payload_len > kReadBufferSize) {
+    } else if (fr.payload_len > a.max_payload) {
       status = kDecErrPayloadLen;  // decodefile.rs:118-121
     } else {
       const uint8_t *pl = a.stream + fr.pos + kFrameHeaderLen;
@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(kDecThreads, X3_DEC_MINBLOCKS) decode_frames_k
     // the SMs this kernel leaves idle while its last frames finish); the host combines the two verdicts.  Frames
     // that kernel refuses to read (decodefile.rs:118-121 and truncation) are not decoded either.
     int status = kDecOk;
-    if (fr.pos + kFrameHeaderLen + fr.payload_len <= a.stream_len && fr.payload_len <= kReadBufferSize) {
+    if (fr.pos + kFrameHeaderLen + fr.payload_len <= a.stream_len && fr.payload_len <= a.max_payload) {
       if (fr.samples == 0u || fr.payload_len < 2u) {
         status = kDecErrPanic;
       } else if (fr.out_off + fr.samples > a.pcm_cap) {

@@ -69,6 +69,8 @@ struct DecodeArgs {
                                        // a frame's status is crc_status if that is an error, else frame_status)
   unsigned long long *result;          // [0] first bad frame of either kernel (init ~0), [1] unused
   uint32_t one;                        // 1, opaque to the compiler: x * one + 0 is a register move on the FMA pipe
+  uint32_t max_payload;                // X3_READ_BUFFER_SIZE for a stream (decodefile.rs:118-121); no such limit for
+                                       // decoder::decode_frame on its own
   const uint16_t *crc_tables;
 };
 

@@ -80,7 +80,7 @@ def encode_frame(wav, writer, params, stats):
     pcm = _as_pcm(wav)
     ps = params.c_struct()
     writer.align(2)
-    cap = 24 + 2 * pcm.size + pcm.size // 4 + 64
+    cap = max(int(L.x3_encode_frame_bound(pcm.size, C.byref(ps))), 32)
     out = np.empty(cap, dtype=np.uint8)
     n = C.c_size_t()
     st = _lib.x3_stats()

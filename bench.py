@@ -326,6 +326,11 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     numa_cpus = bind_near_gpu(local_rank)   # before any pinned allocation: first touch puts the pages on that node
+    # stdout carries exactly one JSON line: NCCL prints its version banner there from C code, so fd 1 points at stderr
+    # until the line itself is written
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     pkg = importlib.import_module("x3-rust_b200")
@@ -563,7 +568,10 @@ def main():
     }
     if workloads is not None:
         line["workloads"] = workloads
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     print(json.dumps(line))
+    sys.stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 

@@ -12,6 +12,7 @@
 // Panics of the reference (unreadable file, non-16-bit or non-mono WAV) are std::runtime_error.
 #pragma once
 
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <cstdio>
@@ -169,7 +170,7 @@ void encode(IterChannel<It> &ch, W &writer, bool quiet = false) {  // encoder.rs
 template <class W>
 void encode_frame(const int16_t *wav, size_t n, W &writer, const Parameters &params, std::array<uint64_t, 6> &stats) {  // encoder.rs:175
   x3_params p = params.c_struct();
-  std::vector<uint8_t> out(24 + 2 * n + n / 4 + 64);
+  std::vector<uint8_t> out(std::max<size_t>(x3_encode_frame_bound(n, &p), 32));   // 2.75 bytes per sample at block_len 1
   size_t len = 0;
   x3_stats st;
   writer.align2();

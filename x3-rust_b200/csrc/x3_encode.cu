@@ -612,7 +612,7 @@ __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const __grid
     if (tid == 0) stage_frame_bulk(a.pcm, s00, n0, s_in, mbar);
     if (n0 & 7u) stage_tail_fast(a.pcm, s00, n0, s_in, tid);
   }
-  uint32_t it = 0, par = 0;
+  uint32_t it = 0, par = 0, crc_phase = 0;
   unsigned long long stat_acc = 0;
 #ifdef X3_ENC_TIMING
   long long tacc[12] = {0}, tlast = clock64();
@@ -1011,7 +1011,7 @@ struct StripShared {
 //         read after the window barrier of one iteration may be rewritten early in the next), [8] next frame (slow path),
 //         [10..13) / [13..16) offset and fits of the pending / of the slow frame (slow path), [16..22) stats,
 //         [24 + q] header CRC | payload CRC of the frame in window q, [32 + 4p ..) offset and fits of the pending frame,
-//         [48..50) mbarrier "window flushed", [64..192) bit counts of the strips
+//         [48..58) mbarriers: "window flushed", three "warp total ready", "slices summed"; [64..192) bit counts of the strips
 constexpr int kMiscT = 64, kMiscWords = 192;
 
 // The frame waiting in a window: every thread keeps its description in registers (the values are uniform); only the
@@ -1117,9 +1117,12 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
   const uint16_t *NA = s_N + 64 * (lane & 3), *NB = s_N + 64 * ((lane >> 2) ? 3 + (lane >> 2) : 0);
   if (tid < 6) s_misc[16 + tid] = 0;
   const uint32_t mb_flush = (uint32_t)__cvta_generic_to_shared(s_misc + 48);   // one arrival per warp and iteration
+  const uint32_t mb_tot = mb_flush + 8u, mb_crc = mb_flush + 32u;   // s_misc[50..56): three "total ready", [56..58): "slices summed"
   if (tid == 0) {
     s_misc[8] = atomicAdd(a.ticket, 1u);
     mbar_init(mb_flush, 4);
+    for (uint32_t k = 0; k < 3u; k++) mbar_init(mb_tot + 8u * k, 1);
+    mbar_init(mb_crc, 4);
   }
   __syncthreads();
   const uint32_t spf = a.P.spf;
@@ -1128,7 +1131,7 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
   uint32_t f = s_misc[8];
   if (f < a.n_frames) stage_rows(a.pcm + (unsigned long long)f * spf, f == last_f ? last_n : spf, S.rows, S.next, wid, lane);
   unsigned long long stat_acc = 0;
-  uint32_t it = 0, par = 0;
+  uint32_t it = 0, par = 0, crc_phase = 0;
   PendingFrame pend;                                   // the frame not yet written out
   pend.q = 2u; pend.f = 0; pend.n = 0; pend.len = 0;
   uint32_t *row = S.rows + (uint32_t)tid * kRowWords;
@@ -1169,7 +1172,7 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
       }
     }
 
-    // ---- scan of the strips' bit counts: within the warp by shuffles, across warps by a CHAIN of named barriers --
+    // ---- scan of the strips' bit counts: within the warp by shuffles, across warps by a CHAIN of mbarriers --
     // warp w signals "my total is there" and waits only for the warps before it, so an early warp relocates while a
     // late one is still packing (a CTA-wide barrier here cost 15 % of the kernel: the four warps sit on four
     // different schedulers and rarely finish together) ----
@@ -1183,23 +1186,14 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
     s_misc[kMiscT + tid] = T;
     uint32_t *s_V = S.V + (it & 1u) * kMaxSlicesStrip;   // by iteration: the finisher of the previous frame may still read the other one
     if (tid >= 32 && tid < 32 + (int)kMaxSlicesStrip) s_V[tid - 32] = 0u;
+    // "warp w's total and bit counts are there": one mbarrier per warp 0..2, one arrival (lane 0, after the warp has
+    // synchronised), waited for by the warps behind it
     uint32_t wbase = 0;
-    if (wid == 0) {
-      asm volatile("bar.arrive 2, 128;\n" ::: "memory");
-    } else if (wid == 1) {
-      asm volatile("bar.arrive 3, 96;\n" ::: "memory");
-      asm volatile("bar.sync 2, 128;\n" ::: "memory");
-      wbase = s_misc[0];
-    } else if (wid == 2) {
-      asm volatile("bar.arrive 4, 64;\n" ::: "memory");
-      asm volatile("bar.sync 2, 128;\n" ::: "memory");
-      asm volatile("bar.sync 3, 96;\n" ::: "memory");
-      wbase = s_misc[0] + s_misc[1];
-    } else {
-      asm volatile("bar.sync 2, 128;\n" ::: "memory");
-      asm volatile("bar.sync 3, 96;\n" ::: "memory");
-      asm volatile("bar.sync 4, 64;\n" ::: "memory");
-      wbase = s_misc[0] + s_misc[1] + s_misc[2];
+    __syncwarp();
+    if (wid < 3 && lane == 0) mbar_arrive(mb_tot + 8u * (uint32_t)wid);
+    for (int k = 0; k < wid; k++) {
+      mbar_wait(mb_tot + 8u * (uint32_t)k, it & 1u);
+      wbase += s_misc[k];
     }
     const uint32_t O = wbase + incl - T;
     uint32_t *win = S.win + par * kWinStride;
@@ -1238,12 +1232,14 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
       if (f_next < a.n_frames)
         stage_rows(a.pcm + (unsigned long long)f_next * spf, f_next == last_f ? last_n : spf, S.rows, S.next, wid, lane);
       crc_slices(win, 0u, nch, nch, s_V, s_T2, s_N, NA, NB, wid, lane);
+      // (B5) "this warp's slices are summed": every warp arrives, only the finisher waits
+      __syncwarp();
+      if (lane == 0) mbar_arrive(mb_crc);
       if (wid == fin) {
-        asm volatile("bar.sync 1, 128;\n" ::: "memory");   // (B5) all slices are there; the other warps only arrive
+        mbar_wait(mb_crc, crc_phase & 1u);
         if (lane == 0) s_misc[24 + par] = crc_finish(s_V, win, 32u * nch, payload_len, n, s_T2, s_N);
-      } else {
-        asm volatile("bar.arrive 1, 128;\n" ::: "memory");
       }
+      crc_phase++;
       if (pend.q != 2u) flush_pending(a, S, pend, tid, off_slot, pol);
       pend.q = par; pend.f = f; pend.n = n; pend.len = payload_len;
       par ^= 1u;
@@ -1264,12 +1260,13 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
       if (f_next < a.n_frames)
         stage_rows(a.pcm + (unsigned long long)f_next * spf, f_next == last_f ? last_n : spf, S.rows, S.next, wid, lane);
       crc_slices(wq, 0u, nch, nch, s_V, s_T2, s_N, NA, NB, wid, lane);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(mb_crc);
       if (wid == fin) {
-        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        mbar_wait(mb_crc, crc_phase & 1u);
         if (lane == 0) s_misc[24 + q] = crc_finish(s_V, wq, 32u * nch, payload_len, n, s_T2, s_N);
-      } else {
-        asm volatile("bar.arrive 1, 128;\n" ::: "memory");
       }
+      crc_phase++;
       pend.q = q; pend.f = f; pend.n = n; pend.len = payload_len;
       if (q != 3u) par ^= 1u;
       f = f_next;

@@ -502,3 +502,51 @@ def test_c5_dealt_files_first_and_last_frames(pkg, dev, oracle):
             out, length, _ = dev.encode_tensor(pcm, p)
             ref, _ = oracle.encode(oracle.synth(2, 0x58330005 + fi, 96000, n0, spf))
             assert length == ref.size and np.array_equal(out[:length].cpu().numpy(), ref), (fi, n0)
+
+
+def test_streaming_reader_matches_whole_file(pkg, oracle, tmp_path):
+    """X3aReader streams the archive in bounded batches (the reference decodes frame by frame with O(frame) memory,
+    decodefile.rs:201-209): with 48 KiB and 1 MiB batches the frames handed out, the errors raised and the WAV written
+    are those of a single whole-file batch, for a clean file, a file cut inside its last frame and a file with a
+    corrupt payload in the middle."""
+    import wave
+    pcm = oracle.synth(2, 0x58330002, 384000, 384000 - 200000, 700000 + 4321)     # 71 frames, the last one short
+    ref, _ = oracle.x3a_encode(pcm, 384000)
+    clean = ref.tobytes()
+    cut = clean[:len(clean) - 5]                       # fewer than 8 bytes short: the reference's Io quirk
+    bad = bytearray(clean)
+    bad[len(bad) // 2] ^= 0x40                         # payload CRC error in a middle frame
+    for name, blob in (("clean", clean), ("cut", cut), ("bad", bytes(bad))):
+        path = tmp_path / (name + ".x3a")
+        path.write_bytes(blob)
+        results = []
+        for chunk in (1 << 30, 1 << 20, 48 << 10):
+            rd = pkg.X3aReader.open(path, quiet=True, chunk_bytes=chunk)
+            buf = np.empty(pkg.decodefile.X3_WRITE_BUFFER_SIZE, dtype=np.int16)
+            out, err = [], None
+            try:
+                while True:
+                    k = rd.decode_next_frame(buf)
+                    if k is None:
+                        break
+                    out.append(buf[:k].copy())
+            except pkg.X3Error as e:
+                err = e.code
+            rd.close()
+            results.append((np.concatenate(out) if out else np.empty(0, np.int16), err, rd.frame_errors))
+        for r in results[1:]:
+            assert np.array_equal(r[0], results[0][0]) and r[1:] == results[0][1:], name
+        if name == "clean":
+            assert results[0][1] is None and np.array_equal(results[0][0], pcm)
+        if name == "cut":
+            assert results[0][1] == pkg.error.IO and results[0][0].size == 700000
+        if name == "bad":
+            assert results[0][1] == pkg.error.FRAME_HEADER_INVALID_PAYLOAD_CRC and 0 < results[0][0].size < pcm.size
+    # x3a_to_wav with small batches writes the same WAV
+    os.environ["X3_STREAM_CHUNK"] = str(64 << 10)
+    try:
+        pkg.x3a_to_wav(tmp_path / "clean.x3a", tmp_path / "s.wav", quiet=True)
+    finally:
+        del os.environ["X3_STREAM_CHUNK"]
+    with wave.open(str(tmp_path / "s.wav"), "rb") as w:
+        assert np.array_equal(np.frombuffer(w.readframes(w.getnframes()), dtype=np.int16), pcm)

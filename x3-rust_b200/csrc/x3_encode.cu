@@ -840,6 +840,7 @@ constexpr uint32_t kRowsBytes = kStripMaxRows * kRowWords * 4;
 
 // rows of this warp's 32 threads <- global (5120 contiguous bytes of the frame); n = samples of the frame.
 // Coalesced 16-byte cp.async: chunk c of the warp's region goes to row c / 10, behind the row's 16 bytes of padding.
+// (One 160-byte bulk async copy per row, issued by lane 0 onto a per-warp mbarrier, was measured: 1.56 -> 1.93 ms.)
 __device__ __forceinline__ void stage_rows(const int16_t *frame, uint32_t n, uint32_t *s_rows, uint32_t *s_next, int wid,
                                            int lane) {
   const uint32_t w0 = (uint32_t)wid * 32u * kStripSamples;              // first sample of the warp's rows

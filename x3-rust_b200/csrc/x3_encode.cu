@@ -881,7 +881,8 @@ __device__ __forceinline__ void crc_slices(const uint32_t *win, uint32_t c_lo, u
                                            int wid, int lane) {
   if (c_hi <= c_lo) return;
   const uint32_t j_lo = (nch - c_hi) >> 5, j_hi = (nch - 1u - c_lo) >> 5;
-  for (uint32_t j = j_lo + (uint32_t)wid; j <= j_hi; j += 4u) {
+  // slices are dealt from warp 3 down: a fifth slice goes to the warp that is last in the next frame's scan chain
+  for (uint32_t j = j_lo + (3u - (uint32_t)wid); j <= j_hi; j += 4u) {
     const uint32_t e = 32u * j + (uint32_t)lane;
     uint32_t h = 0;
     if (e < nch) {
@@ -1223,6 +1224,8 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
     if (optimistic && (uint32_t)tid < nstrips && ((O + T + 31u) >> 5) <= kWinWords)
       strip_relocate_fast(row, T, O, tid ? s_misc[kMiscT + tid - 1] : 32u, (uint32_t)tid + 1u == nstrips, win);
     if (tid == NTS - 1) s_misc[6 + (it & 1u)] = ticket;
+    // (Letting the warps that are done early copy their share of the pending frame out here, before the barrier, was
+    // measured: 1.56 -> 1.68 ms.)
     __syncthreads();                                   // (B4) window complete; size, ticket and pending offset visible
     const uint32_t total_bits = s_misc[4 + (it & 1u)];
     const uint32_t payload_len = payload_bytes(total_bits);

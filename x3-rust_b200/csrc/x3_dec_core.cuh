@@ -504,10 +504,12 @@ X3_HD int decode_frame_generic(Reader &rd, uint32_t payload_len, int16_t *out, u
   }
   X3_GEN_EMIT(lw)
   uint32_t remaining = samples - 1u;
-  // the reader is topped up at every block start and every <= 16 samples inside a block (<= 34 bytes of payload)
+  // The reader is topped up every 16 .. 18 samples (<= 37 bytes of payload), at a block start or inside a long block,
+  // and never twice in a row: a top-up waits for the copies of the one before it.
+  uint32_t since = 16u;
   while (remaining > 0u) {
     const uint32_t bl = remaining < P.block_len ? remaining : P.block_len;  // decoder.rs:50
-    rd.block_begin();
+    if (since >= 16u) { rd.block_begin(); since = 0u; }
     rd.window(hi, lo);
     const uint32_t ftype = hi >> 30;
     if (ftype == 0u) {
@@ -515,25 +517,32 @@ X3_HD int decode_frame_generic(Reader &rd, uint32_t payload_len, int16_t *out, u
       rd.advance(6);
       if (nb <= 5u) return kDecRetryExact;          // FrameDecodeInvalidBPF: the exact path reports it
       const int32_t half = 1 << (nb - 1u), full = 1 << nb;
-      // as many fields as fit the 32 bits one reader step may consume (2 .. 5), then one step
-      uint32_t i = 0;
-      while (i < bl) {
-        if ((i & 15u) >= 12u && i >= 12u) rd.block_begin();
+      // two fields per reader step (2 * 16 bits at most), every lane in step: the trip counts depend on the block
+      // length only, so the 32 frames of a warp do not diverge
+      for (uint32_t i = 0; i < bl; i += 2u) {
+        if (since >= 16u) { rd.block_begin(); since = 0u; }
+        since += 2u;
         rd.window(hi, lo);
-        uint32_t cum = 0;
-        do {
-          int32_t v = (int32_t)(funnel_l(lo, hi, cum) >> (32u - nb));
+        const bool two = i + 1u < bl;
+        int32_t v = (int32_t)(hi >> (32u - nb));
+        if (nb == 16u) {
+          lw = (int32_t)(int16_t)v;                  // literal block: raw samples
+        } else {
+          if (v > half) v -= full;                   // unsigned_to_i16: strictly greater, decoder.rs:203
+          lw = (int32_t)(int16_t)(lw + v);
+        }
+        X3_GEN_EMIT(lw)
+        if (two) {
+          v = (int32_t)(funnel_l(lo, hi, nb) >> (32u - nb));
           if (nb == 16u) {
-            lw = (int32_t)(int16_t)v;                // literal block: raw samples
+            lw = (int32_t)(int16_t)v;
           } else {
-            if (v > half) v -= full;                 // unsigned_to_i16: strictly greater, decoder.rs:203
+            if (v > half) v -= full;
             lw = (int32_t)(int16_t)(lw + v);
           }
           X3_GEN_EMIT(lw)
-          cum += nb;
-          i++;
-        } while (i < bl && cum + nb <= 32u);
-        rd.advance(cum);
+        }
+        rd.advance(two ? 2u * nb : nb);
       }
     } else {
       rd.advance(2);
@@ -541,26 +550,34 @@ X3_HD int decode_frame_generic(Reader &rd, uint32_t payload_len, int16_t *out, u
       const int32_t inv_len = (int32_t)rice_inv_len(code);
       const uint32_t nbk = ftype == 1u ? 1u : (ftype == 2u ? 2u : 4u);   // decoder.rs:158,180
       const int32_t level = 1 << code;
-      // as many codes as fit the 32 bits one reader step may consume, then one step
-      uint32_t i = 0;
-      while (i < bl) {
-        if ((i & 15u) >= 12u && i >= 12u) rd.block_begin();
+      // two codes per reader step, every lane in step (see above); a pair longer than 32 bits -- possible only for
+      // codes beyond the default thresholds, or malformed -- sends the frame to the exact path
+      bool bad = false;
+      for (uint32_t i = 0; i < bl; i += 2u) {
+        if (since >= 16u) { rd.block_begin(); since = 0u; }
+        since += 2u;
         rd.window(hi, lo);
-        uint32_t cum = 0;
-        do {
-          const uint32_t t = funnel_l(lo, hi, cum);
-          const uint32_t z = clz32(t);
-          const uint32_t nbits = z + nbk;
-          if (nbits > 32u) return kDecRetryExact;    // the zero run (or the bits after it) leave the 32 bits in sight
-          if (cum + nbits > 32u) break;              // next step (never the first code of a step: cum = 0 fits)
-          const uint32_t r = (t << z) >> (32u - nbk);
-          const int32_t iv = ftype == 1u ? (int32_t)z : (int32_t)r + level * ((int32_t)z - 1);
-          if (iv < 0 || iv >= inv_len) return kDecRetryExact;   // OutOfBoundsInverse: the exact path reports it
+        const bool two = i + 1u < bl;
+        uint32_t z = clz32(hi);
+        uint32_t cum = z + nbk;
+        bad = bad || cum > 32u;
+        uint32_t r = shl_safe(hi, z) >> (32u - nbk);
+        int32_t iv = ftype == 1u ? (int32_t)z : (int32_t)r + level * ((int32_t)z - 1);
+        bad = bad || iv < 0 || iv >= inv_len;        // OutOfBoundsInverse: the exact path reports it
+        lw = (int32_t)(int16_t)(lw + unfold((uint32_t)iv));
+        X3_GEN_EMIT(lw)
+        if (two) {
+          const uint32_t t = funnel_l(lo, hi, cum > 32u ? 32u : cum);
+          z = clz32(t);
+          cum += z + nbk;
+          bad = bad || cum > 32u;
+          r = shl_safe(t, z) >> (32u - nbk);
+          iv = ftype == 1u ? (int32_t)z : (int32_t)r + level * ((int32_t)z - 1);
+          bad = bad || iv < 0 || iv >= inv_len;
           lw = (int32_t)(int16_t)(lw + unfold((uint32_t)iv));
           X3_GEN_EMIT(lw)
-          cum += nbits;
-          i++;
-        } while (i < bl);
+        }
+        if (bad) return kDecRetryExact;
         rd.advance(cum);
       }
     }

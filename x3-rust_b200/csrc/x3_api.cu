@@ -716,26 +716,39 @@ namespace {
 constexpr int kRetryLargerTable = 1000;   // internal: the frame table / tile candidate capacity was too small
 int decode_device_attempt(const uint8_t *d_frames, size_t len, const x3_params *p, int16_t *d_pcm, size_t pcm_cap,
                           size_t *n_out, x3_decode_result *res, void *cuda_stream, unsigned long long *consumed,
-                          uint32_t tile_bytes, unsigned long long max_frames);
+                          uint32_t tile_bytes, bool hop, unsigned long long max_frames);
 
-// The frame table is sized for frames of 256 bytes and more (the default frame is ~4.7 KB) and the index scans 128 KiB
-// tiles with room for 1024 candidates each.  A stream of smaller frames (small blocks_per_frame: the reference accepts
-// any, decoder.rs:49-55) overflows one or the other; it is then decoded again with 16 KiB tiles and a table for the
-// smallest frame there is (20 + 2 bytes).
+// First attempt: the hop index (64 KiB tiles, at most 64 frames in a tile) with a frame table sized for frames of 256
+// bytes and more (the default frame is ~4.7 KB).  A stream of smaller frames (small blocks_per_frame: the reference
+// accepts any, decoder.rs:49-55) overflows one or the other; it is then indexed by the scan kernel with 16 KiB tiles
+// and a table for the smallest frame there is (20 + 2 bytes).  X3_INDEX=scan skips the hop index (for comparison).
+static bool use_scan_index() {
+  static const bool v = [] { const char *e = getenv("X3_INDEX"); return e && strcmp(e, "scan") == 0; }();
+  return v;
+}
+static uint32_t hop_tile_bytes() {  // X3_HOP_TILE=<KiB> for tuning runs
+  static const uint32_t v = [] {
+    const char *e = getenv("X3_HOP_TILE");
+    const long k = e ? atol(e) : 0;
+    return k >= 1 && k <= 1024 ? (uint32_t)k * 1024u : kHopTileBytes;
+  }();
+  return v;
+}
 int decode_device_impl(const uint8_t *d_frames, size_t len, const x3_params *p, int16_t *d_pcm, size_t pcm_cap,
                        size_t *n_out, x3_decode_result *res, void *cuda_stream, unsigned long long *consumed) {
   unsigned long long max_frames = len / 256 + 4096;
   const unsigned long long most = len / 22 + 1;
   if (max_frames > most) max_frames = most;
-  int rc = decode_device_attempt(d_frames, len, p, d_pcm, pcm_cap, n_out, res, cuda_stream, consumed, kScanTileBytes, max_frames);
+  int rc = decode_device_attempt(d_frames, len, p, d_pcm, pcm_cap, n_out, res, cuda_stream, consumed,
+                                 use_scan_index() ? kScanTileBytes : hop_tile_bytes(), !use_scan_index(), max_frames);
   if (rc == kRetryLargerTable)
-    rc = decode_device_attempt(d_frames, len, p, d_pcm, pcm_cap, n_out, res, cuda_stream, consumed, kScanTileBytesSmall, most);
+    rc = decode_device_attempt(d_frames, len, p, d_pcm, pcm_cap, n_out, res, cuda_stream, consumed, kScanTileBytesSmall, false, most);
   return rc;
 }
 
 int decode_device_attempt(const uint8_t *d_frames, size_t len, const x3_params *p, int16_t *d_pcm, size_t pcm_cap,
                           size_t *n_out, x3_decode_result *res, void *cuda_stream, unsigned long long *consumed,
-                          uint32_t tile_bytes, unsigned long long max_frames) {
+                          uint32_t tile_bytes, bool hop, unsigned long long max_frames) {
   if (consumed) *consumed = 0;
   Derived d;
   int rc = derive(p, &d);
@@ -765,7 +778,7 @@ int decode_device_attempt(const uint8_t *d_frames, size_t len, const x3_params *
   if ((rc = pinned(&host_res))) return rc;
 
   const uint32_t n_tiles = (uint32_t)((len + tile_bytes - 1) / tile_bytes);
-  const bool can_retry = tile_bytes != kScanTileBytesSmall;
+  const bool can_retry = hop || tile_bytes != kScanTileBytesSmall;
   // workspace layout
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
@@ -848,7 +861,7 @@ int decode_device_attempt(const uint8_t *d_frames, size_t len, const x3_params *
   t_all.start();
   if (!need_walk) {
     t_idx.start();
-    e = launch_scan(sa, st);
+    e = launch_scan(sa, hop, st);
     if (e == cudaSuccess) e = launch_chain_check(sa, st);
     t_idx.stop();
     g_launches += 4;

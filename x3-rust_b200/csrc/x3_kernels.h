@@ -95,7 +95,8 @@ struct ScanArgs {
 };
 constexpr uint32_t kScanTileBytes = 128 * 1024;
 constexpr uint32_t kScanTileBytesSmall = 16 * 1024;   // >= 22 bytes per frame: at most 745 frames per tile, under the cap
-cudaError_t launch_scan(const ScanArgs &a, cudaStream_t stream);
+constexpr uint32_t kHopTileBytes = 64 * 1024;         // hop index: one warp per tile, at most 64 frames in a tile
+cudaError_t launch_scan(const ScanArgs &a, bool hop, cudaStream_t stream);  // hop: follow the headers instead of reading every byte
 cudaError_t launch_chain_check(const ScanArgs &a, cudaStream_t stream);
 
 cudaError_t launch_synth(int kind, uint32_t seed, uint32_t fs, unsigned long long n0, unsigned long long count,

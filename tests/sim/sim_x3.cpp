@@ -403,31 +403,47 @@ int sim_encode(const int16_t *pcm, size_t n, const uint32_t *params /*bl,bpf,c0,
 }
 
 // The decoder's table bank against the reference's definition (decoder.rs:157-191, x3.rs:200-252): for every zero
-// run z the 32-bit peek can see and every suffix r whose terminator bit is set, q = z*2^nbk + r must map to
-// INV_RICE_CODE[r + level*(z-1)] when that index is inside the code's table (inv_len 16 / 26 / 60) and must be
-// >= inv_q_end otherwise; q must be monotone in the index.  Returns 0 when everything holds, else a failure code.
+// run z the 32-bit peek can see, every suffix r whose terminator bit is set and every filler below it, the window t
+// must give Q = bits(float(t), toward zero) >> (24 - nbk) whose entry is INV_RICE_CODE[r + level*(z-1)] when that
+// index is inside the code's table (inv_len 16 / 26 / 60) and kInvBad otherwise, and the multiply-high step must move
+// the position by exactly z + nbk.  The valid entries of the three tables must lie in disjoint shared-memory banks.
+// Returns 0 when everything holds, else a failure code.
 int sim_inv_table_check() {
   const int inv_len[4] = {0, 16, 26, 60};
+  uint32_t banks_used = 0;
   for (int f = 1; f <= 3; f++) {
     const RiceBlockPar bp = rice_block_par((uint32_t)f);
-    const int nbk = (int)bp.nbk, level = 1 << (nbk - 1);
-    if (bp.sh != 32u - bp.nbk || bp.q_end != inv_q_end((uint32_t)f)) return 10 + f;
-    if (bp.tab_off != (uint32_t)((f - 1) * kInvTabLen + kInvPad)) return 20 + f;
-    int last_i = -1;
+    const int nbk = (int)inv_nbk((uint32_t)f), level = 1 << (nbk - 1);
+    if (bp.sh != 24u - (uint32_t)nbk || bp.rc != 0u - (158u + (uint32_t)nbk) || bp.tab_off != inv_tab_off((uint32_t)f)) return 10 + f;
+    uint32_t banks = 0;
     for (int z = 0; z <= 31; z++)
-      for (int r = level; r < (1 << nbk); r++) {
-        const int q = (z << nbk) + r, i = r + level * (z - 1);
-        if (q + kInvPad >= kInvTabLen) return 30 + f;          // must stay inside the table
-        if (i <= last_i) return 40 + f;                        // q order == index order
-        last_i = i;
-        const bool valid = i >= 0 && i < inv_len[f];
-        if (valid != ((uint32_t)q < bp.q_end)) return 50 + f;
-        if (valid && (int)inv_tab_entry(f, q + kInvPad) != unfold((uint32_t)i)) return 60 + f;
-      }
-    for (int q = -kInvPad; q < 0; q++)                          // the pad an all-zero peek lands in
-      if (inv_tab_entry(f, q + kInvPad) != 0) return 70 + f;
+      for (int r = level; r < (1 << nbk); r++)
+        for (int fill = 0; fill < 3; fill++) {
+          if (z + nbk > 32) continue;
+          const int below = 32 - z - nbk;   // bits of the window after the code
+          const uint32_t rest = below == 0 ? 0u : (fill == 0 ? 0u : fill == 1 ? (below == 32 ? ~0u : (1u << below) - 1u) : (0x9e3779b9u >> (32 - below)));
+          const uint32_t t = (uint32_t)(((uint64_t)r << below) | rest);
+          const uint32_t fb = f32_rz_bits(t);
+          const uint32_t Q = fb >> bp.sh;
+          if (bp.tab_off + Q >= (uint32_t)kInvTabEntries) return 30 + f;     // must stay inside the bank
+          const int i = r + level * (z - 1);
+          const bool valid = i < inv_len[f];
+          const int d = (int)inv_tab_entry((int)(bp.tab_off + Q));
+          if (valid ? d != unfold((uint32_t)i) : d != kInvBad) return 40 + f;
+          uint32_t left = 32u;
+          left = mad_hi_u32(fb, 512u, left + bp.rc);
+          if (left != 32u - (uint32_t)(z + nbk)) return 50 + f;
+          if (valid) banks |= 1u << (((bp.tab_off + Q) >> 2) & 31u);
+        }
+    if (inv_tab_entry((int)bp.tab_off) != kInvBad) return 60 + f;          // an all-zero peek: float 0, Q = 0
+    if (banks & banks_used) return 70 + f;
+    banks_used |= banks;
   }
-  if (rice_block_par(0).q_end != 1u) return 80;                 // the opaque constant 1 of X3_CUM_ADD
+  for (int j = 0; j < kInvTabEntries; j++) {                              // nothing but deltas and kInvBad
+    const int d = inv_tab_entry(j);
+    if (d != kInvBad && (d < -30 || d > 30)) return 80;
+  }
+  if (rice_block_par(0).one != 1u) return 90;
   return 0;
 }
 
@@ -455,7 +471,7 @@ int sim_decode_frame(const uint8_t *stream, size_t stream_len, size_t pos, uint3
     PlainBitReader rd;
     rd.init(pl, stream + stream_len);
     static inv_entry_t inv[kInvTabEntries];
-    for (int j = 0; j < kInvTabEntries; j++) inv[j] = inv_tab_entry(1 + j / kInvTabLen, j % kInvTabLen);
+    for (int j = 0; j < kInvTabEntries; j++) inv[j] = inv_tab_entry(j);
     RiceBlockPar par[4];
     for (uint32_t f = 0; f < 4; f++) par[f] = rice_block_par(f);
     r = decode_frame_fast(rd, payload_len, out, samples, stage, 1u, inv, par);

@@ -223,46 +223,72 @@ X3_HD bool frame_fast_eligible(uint32_t samples, uint32_t payload_len, uintptr_t
 
 // Inverse-fold tables of the fast path.  A Rice code is z zeros, then nbk = k+1 bits r whose first bit is the
 // terminator; the reference's index is i = r + level*(z-1) with level = 2^k (decoder.rs:157-165, :184-191) and the
-// delta is INV_RICE_CODE[i] (x3.rs:200-204).  The kernel tracks q = z * 2^nbk + r instead -- the low word of the
-// funnel shift (z : t << z) >> (32 - nbk), ONE instruction once z is known -- and looks the delta up by q: entry
-// [q + kInvPad] of table f (f = ftype 1..3: nbk 1, 2, 4).  q is monotone in i over the codes that can occur
-// (r >= level, because t << z has its top bit set), so "some index out of range" is "max q >= inv_q_end(f)".
-// z is at most 31 when the 32-bit peek contains a one; an all-zero peek gives z = 0xffffffff on the device, for which
-// q is -2^nbk as a signed number (inside the pad, and huge as an unsigned one), and z = 32 on the host (q = 2^(nbk+5)).
-// Either way the frame goes to the exact path.
-constexpr int kInvPad = 16;
-constexpr int kInvTabLen = kInvPad + 512 + 8;      // per ftype
-constexpr int kInvTabEntries = 3 * kInvTabLen;
-// Entries are ONE BYTE (every delta of a valid index fits: |INV_RICE_CODE[i]| <= 30 for i < 60): with four entries per
-// 32-bit word the valid q of a table span at most 32 words (k=3: q <= 123), so two lanes that look up different
-// codes never hit different words of the same bank -- the lookups are free of bank conflicts.  (With 16-bit entries
-// the zero runs z and z+4 of a k=3 block collided.)
+// delta is INV_RICE_CODE[i] (x3.rs:200-204).
+//
+// The kernel never computes z.  The 32 bits t that start at the code are converted to a float, rounding toward zero
+// (I2FP.F32.U32.RZ, an ALU-pipe instruction of ~5 cycles; counting leading zeros is an XU instruction of ~23): the
+// float's exponent field is e = 158 - z and its mantissa starts with the bits that follow the terminator, so
+//   Q = bits(float(t)) >> (24 - nbk) = e * level + (r - level)          (one shift)
+// names the code, and the bit position moves on by z + nbk = nbk + 158 - (bits >> 23), which is one IMAD.HI
+// (bits * 512 >> 32, plus the rest as the addend) on the otherwise idle FMA pipe.  The chain from one code to the next
+// (the compiler turns the constant multiply into LEA.HI; a real IMAD.HI, and Q as a multiply-high with the table offset
+// as addend, were measured slower: 1.21 -> 1.38 and 1.23 ms).  The chain from one code to the next is shift -> convert
+// -> shift-add -> add: 24 cycles instead of the 39 of shift -> count -> add (tools/ubench/latency.cu).
+// The delta is looked up by Q: entry [inv_tab_off(f) + Q] of the bank, f = ftype 1..3 (nbk 1, 2, 4).  i = (r - level)
+// + level * z.  Every Q that is not a code of the table (index >= inv_len = 16 / 26 / 60: decoder.rs:161,187; an
+// all-zero peek, for which the float is 0 and Q = 0) holds kInvBad, which no delta equals (|INV_RICE_CODE[i]| <= 30
+// for i < 60): the block keeps the minimum of its deltas and a frame that saw kInvBad goes to the exact path.
+//
+// Entries are ONE BYTE, and the offsets of the three tables are chosen so that the entries of valid codes lie in
+// disjoint banks: f = 3 (Q 1208..1271) in banks 0..15, f = 2 (Q 292..317) in banks 16..23, f = 1 (Q 143..158) in
+// banks 24..28.  Lanes decode unrelated frames, so their lookups hit different tables and different codes at the same
+// time; this layout keeps them free of bank conflicts.
 typedef int8_t inv_entry_t;
-X3_HD inv_entry_t inv_tab_entry(int f /*1..3*/, int j /*0..kInvTabLen*/) {
-  const int nbk = f == 1 ? 1 : (f == 2 ? 2 : 4), level = 1 << (nbk - 1);
-  const int q = j - kInvPad;
-  if (q < 0) return 0;
-  const int z = q >> nbk, r = q & ((1 << nbk) - 1);
-  const int i = r + level * (z - 1);
-  return (i < 0 || i >= 64) ? (inv_entry_t)0 : (inv_entry_t)unfold((uint32_t)i);   // i >= inv_len is flagged via q_end
+constexpr int kInvBad = -128;
+constexpr int kInvExpBias = 158;                    // exponent field of float(t) for a t with bit 31 set
+constexpr int kInvOff1 = 84, kInvOff2 = 288, kInvOff3 = 712;
+constexpr int kInvTabEntries = kInvOff3 + (kInvExpBias + 1) * 8;   // 1984
+X3_HD uint32_t inv_tab_off(uint32_t f) { return f == 1u ? (uint32_t)kInvOff1 : (f == 2u ? (uint32_t)kInvOff2 : (uint32_t)kInvOff3); }
+X3_HD uint32_t inv_nbk(uint32_t f) { return f == 1u ? 1u : (f == 2u ? 2u : 4u); }
+X3_HD uint32_t inv_len_of(uint32_t f) { return f == 1u ? 16u : (f == 2u ? 26u : 60u); }   // x3.rs:214,222,250
+X3_HD inv_entry_t inv_tab_entry(int j /* 0..kInvTabEntries */) {
+  for (uint32_t f = 1; f <= 3; f++) {
+    const int level = 1 << (inv_nbk(f) - 1u);
+    const int Q = j - (int)inv_tab_off(f);
+    if (Q < 0 || Q >= (kInvExpBias + 1) * level) continue;
+    const int z = kInvExpBias - Q / level, i = Q % level + level * z;
+    return (z > 31 || i >= (int)inv_len_of(f)) ? (inv_entry_t)kInvBad : (inv_entry_t)unfold((uint32_t)i);
+  }
+  return (inv_entry_t)kInvBad;   // between the tables
 }
-// first q (with r >= level) whose index i reaches inv_len = 16, 26, 60 (x3.rs:214,222,250):
-//   k=0: i = z        -> z = 16, r = 1;   k=1: i = r + 2(z-1) -> z = 13, r = 2;   k=3: i = r + 8(z-1) -> z = 7, r = 12
-X3_HD uint32_t inv_q_end(uint32_t f) { return f == 1u ? 33u : (f == 2u ? 54u : 124u); }
+
+// bits of (float)t rounded toward zero
+X3_HD uint32_t f32_rz_bits(uint32_t t) {
+#if defined(__CUDA_ARCH__)
+  float f;
+  asm("cvt.rz.f32.u32 %0, %1;" : "=f"(f) : "r"(t));
+  return __float_as_uint(f);
+#else
+  if (t == 0u) return 0u;
+  const uint32_t z = (uint32_t)__builtin_clz(t);
+  return (((uint32_t)kInvExpBias - z) << 23) | (((t << z) >> 8) & 0x7fffffu);
+#endif
+}
 
 // per-ftype constants of a Rice block, fetched with one 16-byte load
 struct alignas(16) RiceBlockPar {
-  uint32_t nbk;       // bits read after the zero run (decoder.rs:158,180)
-  uint32_t sh;        // 32 - nbk
-  uint32_t q_end;     // inv_q_end
-  uint32_t tab_off;   // entry of q = 0 in the table bank
+  uint32_t rc;        // -(158 + nbk): what a code adds to the bits left in the window, apart from its exponent field
+  uint32_t sh;        // 24 - nbk
+  uint32_t one;       // 1 (opaque to the compiler; entry 0 only)
+  uint32_t tab_off;   // entry of Q = 0 in the table bank
 };
 X3_HD RiceBlockPar rice_block_par(uint32_t f) {
   RiceBlockPar p;
-  p.nbk = f == 1u ? 1u : (f == 2u ? 2u : 4u);
-  p.sh = 32u - p.nbk;
-  p.q_end = f ? inv_q_end(f) : 1u;   // entry 0 is never a Rice block: its q_end carries the constant 1 (see X3_CUM_ADD)
-  p.tab_off = (f ? f - 1u : 0u) * (uint32_t)kInvTabLen + (uint32_t)kInvPad;
+  const uint32_t nbk = inv_nbk(f ? f : 1u);
+  p.rc = 0u - ((uint32_t)kInvExpBias + nbk);
+  p.sh = 24u - nbk;
+  p.one = 1u;
+  p.tab_off = inv_tab_off(f ? f : 1u);
   return p;
 }
 
@@ -307,6 +333,10 @@ X3_HD uint32_t max3u(uint32_t a, uint32_t b, uint32_t c) {  // VIMNMX3
   const uint32_t m = a > b ? a : b;
   return m > c ? m : c;
 }
+X3_HD int32_t min3s(int32_t a, int32_t b, int32_t c) {  // VIMNMX3
+  const int32_t m = a < b ? a : b;
+  return m < c ? m : c;
+}
 X3_HD uint32_t pack_lo16(uint32_t lo, uint32_t hi) {  // (lo & 0xffff) | (hi << 16)
 #if defined(__CUDA_ARCH__)
   return __byte_perm(lo, hi, 0x5410);
@@ -315,21 +345,14 @@ X3_HD uint32_t pack_lo16(uint32_t lo, uint32_t hi) {  // (lo & 0xffff) | (hi << 
 #endif
 }
 
-// cum + z + nbk: one IADD3 on the ALU pipe, or (X3_DEC_CUMFMA) two IMADs against an opaque 1 on the FMA pipe
-// (measured: 1.261 -> 1.289 ms, the extra instruction costs more than the ALU slot it frees)
-#if defined(__CUDA_ARCH__) && defined(X3_DEC_CUMFMA)
-#define X3_CUM_ADD(c, z, k) mad_lo_u32((z), one_, mad_lo_u32((k), one_, (c)))
-#else
-#define X3_CUM_ADD(c, z, k) ((c) + (z) + (k))
-#endif
-// one Rice code at offset `cum` of the 64-bit window: q = z * 2^nbk + r (see the table comment), delta = tab[q]
-#define X3_RICE_SAMPLE(qv)                                                            \
+// one Rice code of the 64-bit window hi:lo, `left` bits before the window's end (left = 32 - offset): see the table
+// comment.  left only ever decreases; once it is negative the (clamped) shift shows hi again and the block is flagged.
+#define X3_RICE_SAMPLE(dv)                                                            \
   {                                                                                   \
-    const uint32_t t = funnel_l(lo, hi, cum);                                         \
-    const uint32_t z = clz_shift(t);                                                  \
-    qv = funnel_r(shl_safe(t, z), z, bp.sh);                                          \
-    cum = X3_CUM_ADD(cum, z, bp.nbk);                                                 \
-    lw += (int32_t)tab[(int32_t)qv];                                                  \
+    const uint32_t fb = f32_rz_bits(funnel_r(lo, hi, left));                          \
+    left = mad_hi_u32(fb, 512u, left + bp.rc);                                        \
+    dv = (int32_t)tab[fb >> bp.sh];                                                   \
+    lw += dv;                                                                         \
   }
 
 // Decode one frame.  `stage` = this thread's staging area: 40 words, `ss` words apart.
@@ -361,10 +384,8 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
       // ---- Rice block: z zeros, then nbk bits of which the first is the terminator ----
       rd.advance(2);
       const RiceBlockPar bp = par[ftype];
-      const uint32_t one_ = par[0].q_end;   // rice_block_par(0).q_end is repurposed: it holds 1, opaque to the compiler
-      (void)one_;
       const inv_entry_t *tab = inv_tab + bp.tab_off;
-      uint32_t max_ip = 0, cmax = 0;
+      int32_t dmin = 0, lmin = 0;
       // samples x0..x19; output words (prev,x0) (x1,x2) ... (x17,x18); x19 becomes prev.
       // A valid code is at most 10 bits, so X3_DEC_GROUP = 3 codes fit the 32 bits one reader step may consume.
       // (Four codes per window -- the fourth starts at most 30 bits in, and 32 bits are visible from there, with a
@@ -374,36 +395,33 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
 #define X3_DEC_GROUP 3
 #endif
       constexpr int G = X3_DEC_GROUP, NG = (20 + G - 1) / G;
+      static_assert(G <= 3, "a reader step consumes at most 32 bits");
 #pragma unroll
       for (int g = 0; g < NG; g++) {
         rd.window(hi, lo);
-        uint32_t cum = 0, q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+        uint32_t left = 32u;
+        int32_t d0 = 0, d1 = 0, d2 = 0;
 #pragma unroll
         for (int j = 0; j < G; j++) {
           const int i = G * g + j;
           if (i < 20 && (i < 19 || !tail)) {
-            if (j == 0) X3_RICE_SAMPLE(q0)
-            else if (j == 1) X3_RICE_SAMPLE(q1)
-            else if (j == 2) X3_RICE_SAMPLE(q2)
-            else X3_RICE_SAMPLE(q3)
+            if (j == 0) X3_RICE_SAMPLE(d0)
+            else if (j == 1) X3_RICE_SAMPLE(d1)
+            else X3_RICE_SAMPLE(d2)
             if ((i & 1) == 0) st[(i >> 1) * ss] = pack_lo16(prev, (uint32_t)lw);
             else prev = (uint32_t)lw;
           }
         }
-        const uint32_t m012 = max3u(q0, q1, q2);
-        max_ip = max3u(max_ip, m012, q3);
-        cmax = cum > cmax ? cum : cmax;
-        // the reader moves by at most one word per call; four long codes (33..40 bits) are rare
-        if (G > 3) {
-          if (cum > 32u) { rd.advance(32u); cum -= 32u; }
-        }
-        rd.advance(cum);  // a group longer than 40 bits is malformed for this path (`bad` below); the reader stays
-                          // inside its ring whatever it is given
+        dmin = min3s(dmin, d0, d1);
+        dmin = dmin < d2 ? dmin : d2;
+        lmin = lmin < (int32_t)left ? lmin : (int32_t)left;
+        rd.advance(32u - left);  // more than 32 bits is malformed for this path (`bad` below); the reader stays inside
+                                 // its ring whatever it is given
       }
       // out-of-range index (decoder.rs:161,187; includes every zero run the 32-bit peek cannot see the end of)
-      // or a group of codes longer than 40 bits (its later codes were parsed from the wrong place) -> the exact
+      // or a group of codes longer than 32 bits (its later codes were parsed from the wrong place) -> the exact
       // path decides
-      if (max_ip >= bp.q_end || cmax > (G > 3 ? 40u : 32u)) bad = true;
+      if (dmin == kInvBad || lmin < 0) bad = true;
     } else {
       const uint32_t nb = ((hi >> 26) & 15u) + 1u;  // decoder.rs:211
       rd.advance(6);

@@ -612,7 +612,7 @@ __global__ void __launch_bounds__(kDecThreads, X3_DEC_MINBLOCKS) decode_frames_k
   __shared__ __align__(16) inv_entry_t s_inv[kInvTabEntries];
   __shared__ RiceBlockPar s_par[4];
   const int tid = threadIdx.x;
-  for (int j = tid; j < kInvTabEntries; j += kDecThreads) s_inv[j] = inv_tab_entry(1 + j / kInvTabLen, j % kInvTabLen);
+  for (int j = tid; j < kInvTabEntries; j += kDecThreads) s_inv[j] = inv_tab_entry(j);
   if (tid < 4) s_par[tid] = rice_block_par((uint32_t)tid);
   __syncthreads();
   const unsigned long long n = *a.n_frames < a.max_frames ? *a.n_frames : a.max_frames;

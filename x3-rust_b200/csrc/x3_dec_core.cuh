@@ -387,36 +387,46 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
       const inv_entry_t *tab = inv_tab + bp.tab_off;
       int32_t dmin = 0, lmin = 0;
       // samples x0..x19; output words (prev,x0) (x1,x2) ... (x17,x18); x19 becomes prev.
-      // A valid code is at most 10 bits, so X3_DEC_GROUP = 3 codes fit the 32 bits one reader step may consume.
-      // (Four codes per window -- the fourth starts at most 30 bits in, and 32 bits are visible from there, with a
-      // second reader step for groups of 33..40 bits -- executes fewer instructions but was measured 3 % slower: the
-      // next window then waits for a longer chain.)
+      // X3_DEC_GROUP codes per reader step.  The codes of a group but the last must end inside the first 32 bits of
+      // the window (the peek of the next one starts there); the last may run into the second word, and the reader
+      // then moves in two steps.  Codes the encoder writes are at most 10 bits (20 > thresholds, x3.rs:33-40), a
+      // valid code at most 16: three of the former always fit, longer ones send the frame to the exact path.
+      // (Four per step execute fewer instructions but were measured slower, 1.21 -> 1.26 ms on C2 and 0.29 -> 0.37 ms
+      // on C1: the next window waits for a longer chain.)
 #ifndef X3_DEC_GROUP
 #define X3_DEC_GROUP 3
 #endif
       constexpr int G = X3_DEC_GROUP, NG = (20 + G - 1) / G;
-      static_assert(G <= 3, "a reader step consumes at most 32 bits");
+      static_assert(G == 3 || G == 4, "codes per reader step");
 #pragma unroll
       for (int g = 0; g < NG; g++) {
         rd.window(hi, lo);
         uint32_t left = 32u;
-        int32_t d0 = 0, d1 = 0, d2 = 0;
+        int32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
 #pragma unroll
         for (int j = 0; j < G; j++) {
           const int i = G * g + j;
           if (i < 20 && (i < 19 || !tail)) {
+            if (G == 4 && j == 3) lmin = lmin < (int32_t)left ? lmin : (int32_t)left;
             if (j == 0) X3_RICE_SAMPLE(d0)
             else if (j == 1) X3_RICE_SAMPLE(d1)
-            else X3_RICE_SAMPLE(d2)
+            else if (j == 2) X3_RICE_SAMPLE(d2)
+            else X3_RICE_SAMPLE(d3)
             if ((i & 1) == 0) st[(i >> 1) * ss] = pack_lo16(prev, (uint32_t)lw);
             else prev = (uint32_t)lw;
           }
         }
         dmin = min3s(dmin, d0, d1);
-        dmin = dmin < d2 ? dmin : d2;
-        lmin = lmin < (int32_t)left ? lmin : (int32_t)left;
-        rd.advance(32u - left);  // more than 32 bits is malformed for this path (`bad` below); the reader stays inside
-                                 // its ring whatever it is given
+        dmin = G == 4 ? min3s(dmin, d2, d3) : (dmin < d2 ? dmin : d2);
+        if (G == 3) {
+          lmin = lmin < (int32_t)left ? lmin : (int32_t)left;
+          rd.advance(32u - left);  // more than 32 bits is malformed for this path (`bad` below); the reader stays
+                                   // inside its ring whatever it is given
+        } else {
+          uint32_t cum = 32u - left;
+          if (cum > 32u) { rd.advance(32u); cum -= 32u; }
+          rd.advance(cum);
+        }
       }
       // out-of-range index (decoder.rs:161,187; includes every zero run the 32-bit peek cannot see the end of)
       // or a group of codes longer than 32 bits (its later codes were parsed from the wrong place) -> the exact

@@ -385,7 +385,8 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
       rd.advance(2);
       const RiceBlockPar bp = par[ftype];
       const inv_entry_t *tab = inv_tab + bp.tab_off;
-      int32_t dmin = 0, lmin = 0;
+      int32_t dmin = 0, mprev = 0;
+      uint32_t lneg = 0, lprev = 0;   // sign bit: some group ran past its 32 bits
       // samples x0..x19; output words (prev,x0) (x1,x2) ... (x17,x18); x19 becomes prev.
       // X3_DEC_GROUP codes per reader step.  The codes of a group but the last must end inside the first 32 bits of
       // the window (the peek of the next one starts there); the last may run into the second word, and the reader
@@ -407,7 +408,7 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
         for (int j = 0; j < G; j++) {
           const int i = G * g + j;
           if (i < 20 && (i < 19 || !tail)) {
-            if (G == 4 && j == 3) lmin = lmin < (int32_t)left ? lmin : (int32_t)left;
+            if (G == 4 && j == 3) lneg |= left;
             if (j == 0) X3_RICE_SAMPLE(d0)
             else if (j == 1) X3_RICE_SAMPLE(d1)
             else if (j == 2) X3_RICE_SAMPLE(d2)
@@ -416,22 +417,35 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
             else prev = (uint32_t)lw;
           }
         }
-        dmin = min3s(dmin, d0, d1);
-        dmin = G == 4 ? min3s(dmin, d2, d3) : (dmin < d2 ? dmin : d2);
+        // validity is tracked on the ALU pipe, the kernel's busiest, where a min / max costs two slots: one three-way
+        // minimum per group, folded into the block's minimum every second group; `left` only needs its sign, which an
+        // OR keeps (every second group, three-way as well)
+        const int32_t m = G == 4 ? min3s(d0 < d1 ? d0 : d1, d2, d3) : min3s(d0, d1, d2);
         if (G == 3) {
-          lmin = lmin < (int32_t)left ? lmin : (int32_t)left;
+          if (g & 1) {
+            dmin = min3s(dmin, mprev, m);
+            lneg |= lprev | left;
+          } else {
+            mprev = m;
+            lprev = left;
+          }
           rd.advance(32u - left);  // more than 32 bits is malformed for this path (`bad` below); the reader stays
                                    // inside its ring whatever it is given
         } else {
+          dmin = dmin < m ? dmin : m;
           uint32_t cum = 32u - left;
           if (cum > 32u) { rd.advance(32u); cum -= 32u; }
           rd.advance(cum);
         }
       }
+      if (G == 3 && (NG & 1)) {
+        dmin = dmin < mprev ? dmin : mprev;
+        lneg |= lprev;
+      }
       // out-of-range index (decoder.rs:161,187; includes every zero run the 32-bit peek cannot see the end of)
       // or a group of codes longer than 32 bits (its later codes were parsed from the wrong place) -> the exact
       // path decides
-      if (dmin == kInvBad || lmin < 0) bad = true;
+      if (dmin == kInvBad || (int32_t)lneg < 0) bad = true;
     } else {
       const uint32_t nb = ((hi >> 26) & 15u) + 1u;  // decoder.rs:211
       rd.advance(6);

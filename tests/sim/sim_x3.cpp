@@ -447,6 +447,15 @@ int sim_inv_table_check() {
   return 0;
 }
 
+// crc16_fold over `len` payload bytes placed at offset `off` (even) of a 16-byte aligned buffer
+uint32_t sim_crc_fold(const uint8_t *data, uint32_t len, uint32_t off) {
+  std::vector<uint8_t> raw(len + off + 64 + 16, 0xa5);
+  uint8_t *base = raw.data() + ((16 - ((uintptr_t)raw.data() & 15)) & 15);
+  memcpy(base + off, data, len);
+  CrcMemorySource src;
+  return crc16_fold(src, base + off, len);
+}
+
 uint32_t sim_crc(const uint8_t *data, uint32_t len) {  // len even
   std::vector<uint32_t> w((len + 19) / 4 + 4, 0);
   memcpy(w.data(), data, len);

@@ -22,6 +22,7 @@ def sim():
                                "-Wno-unknown-pragmas", "-o", SO, src])
     lib = C.CDLL(SO)
     lib.sim_crc.restype = C.c_uint32
+    lib.sim_crc_fold.restype = C.c_uint32
     return lib
 
 
@@ -66,6 +67,23 @@ def signals(oracle):
 def test_decoder_tables_match_reference_definition(sim):
     """inverse-fold table bank, q_end thresholds and per-ftype LUT of the GPU decoder vs decoder.rs / x3.rs"""
     assert sim.sim_inv_table_check() == 0
+
+
+def test_sim_crc_fold_matches_serial(sim, oracle):
+    """the decoder's payload CRC (word folding with a^16 = a^12 + a^5 + 1, a = x^32) vs crc.rs, every length class and placement"""
+    rng = np.random.default_rng(7)
+    lens = list(range(2, 200, 2)) + [254, 256, 258, 1022, 1024, 1026, 4094, 4096, 4736, 5000, 20376, 32734]
+    for n in lens:
+        d = rng.integers(0, 256, n, dtype=np.uint8)
+        want = oracle.crc16(d)
+        for off in range(0, 16, 2):
+            got = sim.sim_crc_fold(d.ctypes.data_as(C.c_void_p), C.c_uint32(n), C.c_uint32(off))
+            assert got == want, (n, off)
+    for n in (2, 4, 64, 66, 130):       # all-zero and all-ones payloads (the initial value must still count)
+        for fill in (0, 255):
+            d = np.full(n, fill, dtype=np.uint8)
+            for off in (0, 2, 14):
+                assert sim.sim_crc_fold(d.ctypes.data_as(C.c_void_p), C.c_uint32(n), C.c_uint32(off)) == oracle.crc16(d)
 
 
 def test_sim_crc_matches_serial(sim, oracle):

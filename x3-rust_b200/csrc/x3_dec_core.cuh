@@ -173,6 +173,116 @@ X3_HD uint32_t crc16_bytes(const uint16_t *T, const uint8_t *d, uint32_t n) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Payload CRC by folding (decodefile.rs:93-103, crc.rs:44-52), one thread per payload.
+//
+// With P = x^16 + x^12 + x^5 + 1 and a = x^32 mod P:  squaring is an automorphism of GF(2)[x]/P (P is square free), so
+// a = x^(2^5) has the same minimal polynomial as x, i.e.  a^16 = a^12 + a^5 + 1.  A message of 32-bit words
+// w_0 .. w_(n-1) is the polynomial sum w_j a^(n-1-j); keeping it as sixteen words S_15 .. S_0 (sum S_i a^i) and taking
+// in one more word is
+//     S <- S * a + w :   fb = S_15;  S_i <- S_(i-1);  S_12 ^= fb;  S_5 ^= fb;  S_0 = fb ^ w
+// -- the CRC's own shift register, but on whole words: THREE xors per 32 bits of payload, no tables, no shifts (the
+// bytes of a word never mix, so the words are taken as they lie in memory).  The sixteen words left at the end are a
+// 64-byte message with the same remainder, finished by the ordinary word-at-a-time CRC.  The shift S_i <- S_(i-1) is
+// a renaming: the loop is unrolled by sixteen words (64 bytes, four 16-byte loads) and every register index is static.
+// Zero words in front of a message do not change it, so the fold starts at the 16-byte boundary at or before the
+// payload with everything before the payload's first byte masked to zero; the initial value 0xffff of CRC-16/CCITT-
+// FALSE is xored into the first two payload bytes.  What follows the last whole 64-byte block (up to 15 words and
+// a halfword) goes through the ordinary CRC.
+//
+// `payload` 2-byte aligned, `len` even; reads whole aligned 16-byte vectors that contain payload bytes, and nothing
+// outside [payload & ~15, (payload + len + 15) & ~15) -- the caller guarantees those lie inside its buffer.
+// ------------------------------------------------------------------------------------------------
+X3_HD uint32_t crc16_fold_load(const uint8_t *p) {   // little-endian 32-bit word at a 4-byte aligned address
+#if defined(__CUDA_ARCH__)
+  return *reinterpret_cast<const uint32_t *>(p);
+#else
+  return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+#endif
+}
+struct CrcVec { uint32_t w[4]; };
+X3_HD CrcVec crc16_fold_load16(const uint8_t *p) {   // 16-byte aligned
+  CrcVec v;
+#if defined(__CUDA_ARCH__)
+  const uint4 q = *reinterpret_cast<const uint4 *>(p);
+  v.w[0] = q.x; v.w[1] = q.y; v.w[2] = q.z; v.w[3] = q.w;
+#else
+  for (int k = 0; k < 4; k++) v.w[k] = crc16_fold_load(p + 4 * k);
+#endif
+  return v;
+}
+// Where the 64-byte blocks come from.  Concept: void begin(const uint8_t *first_block, uint32_t n_blocks);
+// void block(uint32_t b, CrcVec v[4]) -- block b's four vectors, called for b = 0, 1, .. n_blocks-1 in order.
+struct CrcMemorySource {   // straight from memory (host simulation; the device kernel streams through a ring)
+  const uint8_t *base;
+  X3_HD void begin(const uint8_t *first_block, uint32_t) { base = first_block; }
+  X3_HD void block(uint32_t b, CrcVec v[4]) const {
+#pragma unroll
+    for (int q = 0; q < 4; q++) v[q] = crc16_fold_load16(base + 64u * b + 16 * q);
+  }
+};
+template <class Source>
+X3_HD uint32_t crc16_fold(Source &src, const uint8_t *payload, uint32_t len) {
+  const uintptr_t pa = (uintptr_t)payload;
+  const uint8_t *A16 = payload - (pa & 15u);                 // start of the fold
+  const uint32_t k0 = (uint32_t)(pa & 15u) >> 2;             // word (of the first block) that holds the first payload byte
+  const uint32_t lead = (uint32_t)(pa & 3u);                 // 0 or 2 bytes of that word are not payload
+  const uint32_t span = (uint32_t)(pa & 15u) + len;          // bytes from A16 to the payload's end
+  const uint32_t nwords = span >> 2;                         // whole words from A16 that end inside the payload
+  const uint32_t nb = nwords >> 4;                           // whole 64-byte blocks
+  // the first payload word as the fold wants it: bytes before the payload cleared, 0xffff xored into payload bytes 0, 1
+  const uint32_t first_and = lead ? 0xffff0000u : 0xffffffffu, first_xor = lead ? 0xffff0000u : 0x0000ffffu;
+  const bool has_first_word = nwords > k0;                    // else the payload is a single halfword (len 2, lead 0)
+  uint32_t acc = has_first_word ? 0u : 0xffffu;
+  uint32_t k = k0;                                            // next word (index from A16) for the ordinary CRC
+  if (nb > 0u) {
+    uint32_t R[16];
+    src.begin(A16, nb);
+    {
+      // block 0 into the empty state: S_i = w_(15-i)
+      CrcVec v[4];
+      src.block(0u, v);
+#pragma unroll
+      for (int t = 0; t < 16; t++) {
+        uint32_t w = v[t >> 2].w[t & 3];
+        if ((uint32_t)t < k0) w = 0u;
+        if ((uint32_t)t == k0) w = (w & first_and) ^ first_xor;
+        R[15 - t] = w;
+      }
+    }
+    for (uint32_t b = 1; b < nb; b++) {
+      CrcVec v[4];
+      src.block(b, v);
+#pragma unroll
+      for (int t = 0; t < 16; t++) {
+        const int pi = 15 - t;                                // holds S_15 now, S_0 after this step
+        const uint32_t fb = R[pi];
+        R[(pi + 12) & 15] ^= fb;                              // becomes S_12
+        R[(pi + 5) & 15] ^= fb;                               // becomes S_5
+        R[pi] = fb ^ v[t >> 2].w[t & 3];
+      }
+    }
+#pragma unroll
+    for (int i = 15; i >= 0; i--) acc = crc16_word_alu(acc, bswap32(R[i]));
+    k = 16u * nb;
+  }
+  for (; k < nwords; k++) {
+    uint32_t w = crc16_fold_load(A16 + 4u * k);
+    if (k == k0) w = (w & first_and) ^ first_xor;
+    acc = crc16_word_alu(acc, bswap32(w));
+  }
+  if (span & 2u) {                                            // the payload ends with half a word
+    const uint8_t *h = A16 + 4u * nwords;
+#if defined(__CUDA_ARCH__)
+    const uint32_t v = *reinterpret_cast<const uint16_t *>(h);
+#else
+    const uint32_t v = (uint32_t)h[0] | ((uint32_t)h[1] << 8);
+#endif
+    acc = crc16_half_alu(acc, ((v & 0xffu) << 8) | (v >> 8));
+  }
+  return acc & 0xffffu;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Fast path
 // ------------------------------------------------------------------------------------------------
 

@@ -419,9 +419,87 @@ __device__ __forceinline__ uint32_t load_be32_2aligned(const uint8_t *p) {
   return ((a & 0xff) << 24) | ((a >> 8) << 16) | ((b & 0xff) << 8) | (b >> 8);
 }
 
-#ifndef X3_CRC_THREADS
-#define X3_CRC_THREADS 256   // 128 or 64 (more CTAs beside the decode kernel) were measured: the pair finishes later
+#ifndef X3_CRC_FOLD
+#define X3_CRC_FOLD 1   // 1: one thread per frame, word folding (crc16_fold); 0: one warp per frame, chunk CRCs + combine tree
 #endif
+#ifndef X3_CRC_THREADS
+#define X3_CRC_THREADS (X3_CRC_FOLD ? 64 : 256)
+#endif
+#if X3_CRC_FOLD
+// One thread per frame: three xors per 32-bit word (crc16_fold, x3_dec_core.cuh) instead of the ~26 shifts and xors of
+// the word-at-a-time CRC -- a tenth of the instructions of the warp-per-frame kernel below, which matters because
+// this kernel shares the SMs with decode_frames_kernel (both live on the ALU pipe).  With so little arithmetic the
+// kernel is bound by how many bytes it keeps in flight: every lane streams its payload through a private ring of
+// kCrcRingBlocks 64-byte blocks in shared memory, filled by 16-byte cp.async seven blocks ahead of the fold.
+constexpr int kCrcRingBlocks = 8;
+constexpr int kCrcRowBytes = kCrcRingBlocks * 64 + 16;   // + 16: rows 4 banks apart, 16-byte reads of 8 lanes never collide
+struct CrcRingSource {
+  const uint8_t *base;
+  unsigned char *row;     // this lane's ring
+  uint32_t nb, issued;
+  __device__ __forceinline__ void issue_one() {   // one block, one commit group (empty past the end: the count stays uniform)
+    if (issued < nb) {
+      unsigned char *dst = row + 64u * (issued & (kCrcRingBlocks - 1));
+      const uint8_t *src = base + 64ull * issued;
+#pragma unroll
+      for (int q = 0; q < 4; q++) cp_async16(dst + 16 * q, src + 16 * q);
+    }
+    cp_async_commit();
+    issued++;
+  }
+  __device__ __forceinline__ void begin(const uint8_t *first_block, uint32_t n_blocks) {
+    base = first_block;
+    nb = n_blocks;
+    issued = 0;
+#pragma unroll
+    for (int i = 0; i < kCrcRingBlocks - 1; i++) issue_one();
+  }
+  __device__ __forceinline__ void block(uint32_t b, CrcVec v[4]) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(kCrcRingBlocks - 2) : "memory");   // block b has landed
+    const uint4 *p = reinterpret_cast<const uint4 *>(row + 64u * (b & (kCrcRingBlocks - 1)));
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const uint4 x = p[q];
+      v[q].w[0] = x.x; v[q].w[1] = x.y; v[q].w[2] = x.z; v[q].w[3] = x.w;
+    }
+    issue_one();   // block b + 7 goes to the slot of block b - 1, whose words were consumed before this call
+  }
+};
+__global__ void __launch_bounds__(X3_CRC_THREADS) crc_frames_kernel(const DecodeArgs a) {
+  __shared__ uint16_t s_T[256];  // byte table, for payloads at odd addresses only
+  __shared__ __align__(16) unsigned char s_ring[X3_CRC_THREADS * kCrcRowBytes];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_T[i] = a.crc_tables[i];
+  __syncthreads();
+  const unsigned long long n = *a.n_frames < a.max_frames ? *a.n_frames : a.max_frames;
+  const unsigned long long threads = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long f = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; f < n; f += threads) {
+    const FrameRec fr = a.frames[f];
+    int status = kDecOk;
+    const unsigned long long pend = fr.pos + kFrameHeaderLen + fr.payload_len;
+    if (pend > a.stream_len) {
+      status = kDecErrPanic;  // never produced by the index (truncated frames are dropped); defensive
+    } else if (fr.payload_len > a.max_payload) {
+      status = kDecErrPayloadLen;  // decodefile.rs:118-121
+    } else {
+      const uint8_t *pl = a.stream + fr.pos + kFrameHeaderLen;
+      const uint32_t len = fr.payload_len;
+      uint32_t s;
+      if (((uintptr_t)pl & 1u) || (len & 1u) || len == 0u) {
+        s = crc16_bytes(s_T, pl, len);  // foreign stream: bytewise
+      } else {
+        CrcRingSource src;
+        src.row = s_ring + threadIdx.x * kCrcRowBytes;
+        s = crc16_fold(src, pl, len);
+        cp_async_wait_all();
+      }
+      if ((s & 0xffffu) != fr.payload_crc) status = kDecErrPayloadCrc;  // decodefile.rs:97-100
+    }
+    a.crc_status[f] = status;
+    if (status != kDecOk) atomicMin(a.result, f);
+  }
+}
+#else
+// (128 or 64 threads per CTA -- more CTAs beside the decode kernel -- were measured: the pair finishes later)
 __global__ void __launch_bounds__(X3_CRC_THREADS) crc_frames_kernel(const DecodeArgs a) {
   __shared__ uint16_t s_T[kCrcTableEntries];
   for (int i = threadIdx.x; i < kCrcTableEntries; i += blockDim.x) s_T[i] = a.crc_tables[i];
@@ -490,6 +568,8 @@ __global__ void __launch_bounds__(X3_CRC_THREADS) crc_frames_kernel(const Decode
     }
   }
 }
+
+#endif  // X3_CRC_FOLD
 
 // ------------------------------------------------------------------------------------------------
 // 3. decode, one thread per frame
@@ -695,7 +775,7 @@ cudaError_t launch_crc(const DecodeArgs &a, unsigned long long n_frames_hint, cu
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (n_frames_hint < 1) n_frames_hint = 1;
-  unsigned long long g = (n_frames_hint * 32ull + X3_CRC_THREADS - 1ull) / X3_CRC_THREADS;  // one warp per frame
+  unsigned long long g = (n_frames_hint * (X3_CRC_FOLD ? 1ull : 32ull) + X3_CRC_THREADS - 1ull) / X3_CRC_THREADS;  // one thread / one warp per frame
   const unsigned long long cap = (unsigned long long)sms * (2048ull / X3_CRC_THREADS);
   if (g > cap) g = cap;
   crc_frames_kernel<<<(unsigned)g, X3_CRC_THREADS, 0, stream>>>(a);

@@ -1191,12 +1191,20 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
     // "warp w's total and bit counts are there": one mbarrier per warp 0..2, one arrival (lane 0, after the warp has
     // synchronised), waited for by the warps behind it
     uint32_t wbase = 0;
+#ifdef X3_RACECHECK_BARRIERS
+    // sanitizer build (tools/sanitize_run.sh): compute-sanitizer's racecheck does not follow mbarrier arrive -> wait
+    // ordering (tools/ubench/mbar_racecheck.cu), so this build puts a CTA barrier wherever the product waits on an
+    // mbarrier -- a superset of the product's ordering that racecheck can see; everything else is unchanged
+    __syncthreads();
+    for (int k = 0; k < wid; k++) wbase += s_misc[k];
+#else
     __syncwarp();
     if (wid < 3 && lane == 0) mbar_arrive(mb_tot + 8u * (uint32_t)wid);
     for (int k = 0; k < wid; k++) {
       mbar_wait(mb_tot + 8u * (uint32_t)k, it & 1u);
       wbase += s_misc[k];
     }
+#endif
     const uint32_t O = wbase + incl - T;
     uint32_t *win = S.win + par * kWinStride;
     // The last warp knows the frame's size first: it publishes it (nobody waits for the offset here), decides whether
@@ -1217,7 +1225,11 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
       wait_offset(a, pend.f, (uint32_t)kFrameHeaderLen + pend.len, off_slot, pend_status);
     // The window about to be written is the one the previous iteration copied out at its end: every warp has said
     // "my share is out" on an mbarrier since (a split barrier: the arrival was a whole pack phase ago, so nobody waits).
+#ifdef X3_RACECHECK_BARRIERS
+    __syncthreads();
+#else
     if (it) mbar_wait(mb_flush, (it - 1u) & 1u);
+#endif
     // relocation, before the frame is known to fit the window: a strip that would leave it stays where it is (the
     // frame then takes the slow path, which starts over from the rows)
     const bool optimistic = pend.q != 3u;              // a pending frame that fills both windows must go out first
@@ -1237,10 +1249,15 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
         stage_rows(a.pcm + (unsigned long long)f_next * spf, f_next == last_f ? last_n : spf, S.rows, S.next, wid, lane);
       crc_slices(win, 0u, nch, nch, s_V, s_T2, s_N, NA, NB, wid, lane);
       // (B5) "this warp's slices are summed": every warp arrives, only the finisher waits
+#ifdef X3_RACECHECK_BARRIERS
+      __syncthreads();
+      if (wid == fin) {
+#else
       __syncwarp();
       if (lane == 0) mbar_arrive(mb_crc);
       if (wid == fin) {
         mbar_wait(mb_crc, crc_phase & 1u);
+#endif
         if (lane == 0) s_misc[24 + par] = crc_finish(s_V, win, 32u * nch, payload_len, n, s_T2, s_N);
       }
       crc_phase++;
@@ -1264,10 +1281,15 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
       if (f_next < a.n_frames)
         stage_rows(a.pcm + (unsigned long long)f_next * spf, f_next == last_f ? last_n : spf, S.rows, S.next, wid, lane);
       crc_slices(wq, 0u, nch, nch, s_V, s_T2, s_N, NA, NB, wid, lane);
+#ifdef X3_RACECHECK_BARRIERS
+      __syncthreads();
+      if (wid == fin) {
+#else
       __syncwarp();
       if (lane == 0) mbar_arrive(mb_crc);
       if (wid == fin) {
         mbar_wait(mb_crc, crc_phase & 1u);
+#endif
         if (lane == 0) s_misc[24 + q] = crc_finish(s_V, wq, 32u * nch, payload_len, n, s_T2, s_N);
       }
       crc_phase++;
@@ -1278,8 +1300,10 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
       f = slow_frame(a, S, f, n, T, O, total_bits, pend, spf, last_f, last_n);
       pend.q = 2u;
     }
+#ifndef X3_RACECHECK_BARRIERS
     __syncwarp();
     if (lane == 0) mbar_arrive(mb_flush);              // this warp is done with the windows of this iteration
+#endif
     it++;
     if ((it & 127u) == 0u) {                           // the 10-bit counters (4 blocks per frame) are about to fill up
 #pragma unroll

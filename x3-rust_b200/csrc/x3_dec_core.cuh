@@ -4,16 +4,18 @@
 // block decoders (:147-235), BitReader (bitreader.rs:29-176) and the payload CRC check of
 // decodefile.rs:93-103.  Host+device so tests/sim can run the same source on the CPU.
 //
-// Two paths:
+// Three paths:
 //  * decode_frame_fast  -- Parameters::default() streams with frames of a multiple of 80 samples.  64-bit
-//    shifting bit window refilled once per three Rice codes, terminators by count-leading-zeros, output
-//    staged 160 bytes at a time so every lane writes whole 32-byte sectors.  The payload CRC is checked
-//    by a separate coalesced kernel (x3_decode.cu) before the frame is decoded, as decodefile.rs:93-103 does.  It never trusts a frame it cannot prove well formed: any
-//    zero run >= 32 bits, out-of-range Rice index or bad BFP header makes it give up ...
+//    shifting bit window refilled once per three Rice codes, zero runs from the exponent of a float conversion
+//    (see the table comment below), output staged 160 bytes at a time so every lane writes whole 32-byte sectors.
+//    The payload CRC is checked by a separate kernel (crc16_fold below, x3_decode.cu) beside the decode, as
+//    decodefile.rs:93-103 does before it.  It never trusts a frame it cannot prove well formed: any zero run the
+//    32-bit peek cannot see the end of, out-of-range Rice index or bad BFP header makes it give up ...
+//  * decode_frame_generic -- every frame the tuned path does not cover (other Parameters, short last frame,
+//    unaligned output): same reader, any block_len / codes, closed-form inverse fold; gives up the same way ...
 //  * decode_frame_exact -- ... and the frame is decoded again by a literal restatement of the reference's
 //    word-structured BitReader, which reproduces its behaviour on malformed payloads bit for bit
-//    (short-tail refill, one-word look-ahead in count_zero_bits, zero fill past the end).  Also used for
-//    every frame the fast path does not cover (other Parameters, short last frame, unaligned output).
+//    (short-tail refill, one-word look-ahead in count_zero_bits, zero fill past the end).
 #pragma once
 
 #include "x3_common.cuh"

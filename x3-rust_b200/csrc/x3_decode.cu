@@ -1,16 +1,16 @@
 // x3_decode.cu -- frame index, payload CRC and frame decode kernels for sm_100a.
 //
 // Decode of a device-resident frame stream is stream-ordered, no host round trip before the end:
-//   1. scan_headers_kernel  -- finds every frame header (key 'x3' + header CRC + field checks of
-//      decoder.rs:69-118) at even offsets and hands each 128 KiB tile's frames over in order;
+//   1. hop_index_kernel     -- one warp per 64 KiB tile finds the tile's first frame header (key 'x3' + header CRC +
+//      field checks of decoder.rs:69-118) and follows header -> payload_len -> next header to the tile's end;
 //      tile_prefix_kernel + place_frames_kernel turn the tiles' counts into frame ordinals / sample offsets and
 //      write the dense frame table; check_chain_kernel then proves the table is exactly the header ->
 //      payload_len -> next header walk of decodefile.rs:105-126.  Anything it cannot prove (false candidate,
 //      corrupt header, odd payload length) raises a flag and the API falls back to the sequential host walk,
-//      which reproduces the reference's error behaviour.
-//   2. crc_frames_kernel    -- one warp per frame, coalesced 16-byte chunks, chunk CRCs combined with
-//      multiply-by-x^n tables (same scheme as the encoder): decodefile.rs:93-103.  Runs on a second stream
-//      beside step 3.
+//      which reproduces the reference's error behaviour.  scan_headers_kernel (every even offset tested) indexes
+//      streams of frames too small for the hop index's 64 frames per tile.
+//   2. crc_frames_kernel    -- one thread per frame, word folding (crc16_fold: three xors per 32 bits), payload
+//      streamed through a per-lane cp.async ring: decodefile.rs:93-103.  Runs on a second stream beside step 3.
 //   3. decode_frames_kernel -- one thread per frame (frames are independent, blocks inside a frame are
 //      not): x3_dec_core.cuh.  Every lane streams its own payload through a private 144-byte
 //      shared-memory ring filled by cp.async one block ahead, and writes whole 32-byte sectors (one 256-bit store).

@@ -14,6 +14,8 @@ import time
 import torch
 import torch.distributed as dist
 
+_stdout = os.dup(1)   # NCCL prints its version banner on fd 1: keep the JSON line alone on the real stdout
+os.dup2(2, 1)
 rank = int(os.environ.get("RANK", "0"))
 local = int(os.environ.get("LOCAL_RANK", "0"))
 world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -67,6 +69,6 @@ res["e2e_ceiling_msamples_s"] = alone / 4.0 * 1000.0
 res["note"] = ("e2e ceiling = (slower direction, GB/s, all ranks) / 4 bytes per sample: the encode call is bound by the PCM "
                "upload, the decode call by the PCM download; the compressed stream travels the other way at the same time")
 if rank == 0:
-    print(json.dumps(res))
+    os.write(_stdout, (json.dumps(res) + "\n").encode())
 if world > 1:
     dist.destroy_process_group()

@@ -169,6 +169,10 @@ uint64_t x3_kernel_launch_count(void);
  * thread: [0] encode_frames / decode_frames kernel, [1] frame index (scan + chain check, decode only),
  * [2] whole device section, [3] payload CRC kernel (decode only). */
 int x3_last_kernel_ms(float ms[4]);
+/* Which encode kernel the most recent x3_encode_device call on this thread ran when the choice was made on the
+ * device (Parameters::default() inputs of 64 frames and more): 1 = block-per-thread kernel (inputs dominated by BFP /
+ * literal blocks), 2 = strip kernel; negative when no choice was made (other parameters, small or forced calls). */
+int x3_last_encode_kernel(void);
 
 #ifdef __cplusplus
 }

@@ -66,4 +66,5 @@ extern "C" {
     pub fn x3_synth_device(kind: c_int, seed: u32, fs: u32, n0: u64, count: u64, d_out: *mut i16, stream: *mut c_void) -> c_int;
     pub fn x3_kernel_launch_count() -> u64;
     pub fn x3_last_kernel_ms(ms: *mut f32) -> c_int;
+    pub fn x3_last_encode_kernel() -> c_int;
 }

@@ -234,7 +234,7 @@ def test_device_resident_round_trip(pkg, dev, oracle):
     pcm = dev.synth(2, 0x58330002, 384000, 384000 - 300000, n)
     before = dev.kernel_launch_count()
     out, length, stats = dev.encode_tensor(pcm, p)
-    assert dev.kernel_launch_count() == before + 1
+    assert dev.kernel_launch_count() == before + 3    # the probe (workspace zeroing + kernel choice) and both kernels, one of which returns at once
     ref, rstats = oracle.encode(pcm.cpu().numpy())
     assert length == ref.size and np.array_equal(out[:length].cpu().numpy(), ref) and stats == rstats
     dec, ns, res, code = dev.decode_tensor(out, length, p, max_samples=n)
@@ -402,6 +402,9 @@ def test_full_size_c2_c4_bytes_match_oracle(pkg, dev, oracle, kind, seed):
     p = pkg.x3.Parameters.default()
     pcm = dev.synth(kind, seed, 384000, 0, n)
     out, length, stats = dev.encode_tensor(pcm, p)
+    # the kernel picked on the device: the strip kernel for the hydrophone recording, the block-per-thread kernel for
+    # the stress signal (most of its blocks are BFP / literal, its frames overflow the strip kernel's windows)
+    assert pkg._lib.lib().x3_last_encode_kernel() == (2 if kind == 2 else 1)
     host_pcm = pcm.cpu().numpy()
     ref, rstats = oracle.encode(host_pcm, threads=os.cpu_count() or 8)
     assert length == ref.size and stats == rstats
@@ -550,3 +553,32 @@ def test_streaming_reader_matches_whole_file(pkg, oracle, tmp_path):
         del os.environ["X3_STREAM_CHUNK"]
     with wave.open(str(tmp_path / "s.wav"), "rb") as w:
         assert np.array_equal(np.frombuffer(w.readframes(w.getnframes()), dtype=np.int16), pcm)
+
+
+@pytest.mark.parametrize("kernel", ["strip", "fast"])
+def test_forced_encode_kernels_match_oracle(oracle, kernel, tmp_path):
+    """Both Parameters::default() encode kernels on both kinds of input, whatever the probe would pick
+    (X3_ENC_KERNEL is read once per process, hence the subprocess): frame bytes and statistics equal the oracle's."""
+    import subprocess
+    import sys
+    script = tmp_path / "forced.py"
+    script.write_text(
+        "import importlib, os, sys\n"
+        "import numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "sys.path.insert(0, os.path.join(%r, 'oracle'))\n"
+        "import x3_oracle as o\n"
+        "pkg = importlib.import_module('x3-rust_b200')\n"
+        "dev = importlib.import_module('x3-rust_b200.device')\n"
+        "o.lib()\n"
+        "p = pkg.x3.Parameters.default()\n"
+        "for kind, seed, n in ((2, 0x58330002, 3000000), (4, 0x58330004, 3000000), (2, 0x58330002, 12345), (4, 0x58330004, 654321)):\n"
+        "    pcm = dev.synth(kind, seed, 384000, 0, n)\n"
+        "    out, length, stats = dev.encode_tensor(pcm, p)\n"
+        "    ref, rstats = o.encode(pcm.cpu().numpy(), threads=8)\n"
+        "    assert pkg._lib.lib().x3_last_encode_kernel() < 0 or n < 640000, 'forced call must not probe'\n"
+        "    assert length == ref.size and stats == rstats and np.array_equal(out[:length].cpu().numpy(), ref), (kind, n)\n"
+        "print('ok')\n" % (ROOT, ROOT))
+    env = dict(os.environ, X3_ENC_KERNEL=kernel)
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr

@@ -60,6 +60,7 @@ SYMBOLS = {
     "x3_synth_device": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
     "x3_kernel_launch_count": (C.c_uint64, []),
     "x3_last_kernel_ms": (C.c_int, [_P(C.c_float * 4)]),
+    "x3_last_encode_kernel": (C.c_int, []),
 }
 
 _lib = None

@@ -23,6 +23,7 @@ namespace {
 std::atomic<uint64_t> g_launches{0};
 thread_local char tl_cuda_err[256] = "";
 thread_local float tl_ms[4] = {0.f, 0.f, 0.f, 0.f};
+thread_local int tl_enc_kernel = -1;   // kernel kind of the most recent x3_encode_device on this thread (x3_last_encode_kernel)
 thread_local uint32_t tl_max_payload = x3::kReadBufferSize;   // x3_decode_frame_host lifts the stream reader's limit
 
 int cuda_fail(cudaError_t e, const char *what) {
@@ -169,11 +170,17 @@ struct Derived {
   size_t smem;
 };
 
-// X3_ENC_KERNEL=fast selects the round-1 block-per-thread kernel instead of the strip kernel (A/B measurements)
-bool use_old_fast_kernel() {
-  static const bool v = [] { const char *e = getenv("X3_ENC_KERNEL"); return e && !strcmp(e, "fast"); }();
+// Parameters::default() inputs have two kernels: the strip kernel (ordinary audio) and the block-per-thread kernel of
+// round 1 (inputs whose frames overflow the strip kernel's windows); encode_probe_kernel picks per call.
+// X3_ENC_KERNEL=fast / =strip forces one of them (A/B measurements).
+int forced_kernel() {
+  static const int v = [] {
+    const char *e = getenv("X3_ENC_KERNEL");
+    return !e ? -1 : !strcmp(e, "fast") ? (int)kEncKernelFast : !strcmp(e, "strip") ? (int)kEncKernelStrip : -1;
+  }();
   return v;
 }
+bool use_old_fast_kernel() { return forced_kernel() == (int)kEncKernelFast; }
 size_t encode_smem_of(int kind, const CodecParams &P, uint32_t max_blocks, uint32_t out_words_cap) {
   return kind == kEncKernelStrip ? encode_strip_smem_bytes()
          : kind == kEncKernelFast ? encode_fast_smem_bytes(P, out_words_cap)
@@ -288,6 +295,7 @@ const char *x3_strerror(int code) {
 
 const char *x3_last_cuda_error(void) { return tl_cuda_err; }
 uint64_t x3_kernel_launch_count(void) { return g_launches.load(); }
+int x3_last_encode_kernel(void) { return tl_enc_kernel; }
 int x3_last_kernel_ms(float ms[4]) {
   if (!ms) return X3_ERR_INVALID_ARGUMENT;
   ms[0] = tl_ms[0]; ms[1] = tl_ms[1]; ms[2] = tl_ms[2]; ms[3] = tl_ms[3];
@@ -335,7 +343,7 @@ int x3_read_frame_header(const uint8_t *b, size_t len, x3_frame_header *h) {
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-size_t encode_ws_bytes(unsigned long long nf) { return 128 + 8 * (size_t)nf + 256; }  // + optional phase timing words
+size_t encode_ws_bytes(unsigned long long nf) { return (128 + 8 * (size_t)nf + 256 + 15) & ~(size_t)15; }  // + optional phase timing words
 
 // per-thread resources of the pipelined host path (x3_encode_host)
 struct HostPipe {
@@ -374,8 +382,6 @@ cudaError_t enqueue_encode(Derived d, DeviceState *ds, const int16_t *d_pcm, siz
                            unsigned char *ws, cudaStream_t st, int *rc_out) {
   *rc_out = X3_OK;
   const unsigned long long nf = (n_samples + d.P.spf - 1) / d.P.spf;
-  cudaError_t e = cudaMemsetAsync(ws, 0, encode_ws_bytes(nf), st);
-  if (e != cudaSuccess) return e;
   EncodeArgs a;
   a.pcm = d_pcm;
   a.n_samples = n_samples;
@@ -391,6 +397,7 @@ cudaError_t enqueue_encode(Derived d, DeviceState *ds, const int16_t *d_pcm, siz
   a.timing = reinterpret_cast<unsigned long long *>(ws + 128 + 8 * (size_t)nf);
   a.crc_tables = ds->crc_dev;
   a.neg_one = -1;
+  a.choice = nullptr;
   // the fast kernels stage frames with 16-byte async copies: they need a 16-byte aligned base and frame size (and the
   // strip kernel a 2-byte aligned output: it writes halfwords and 16-byte aligned bulk stores)
   if (d.kind != kEncKernelGeneric && ((((uintptr_t)d_pcm) & 15u) != 0 || ((d.P.spf * 2u) & 15u) != 0 || (((uintptr_t)d_out) & 1u) != 0)) {
@@ -398,25 +405,48 @@ cudaError_t enqueue_encode(Derived d, DeviceState *ds, const int16_t *d_pcm, siz
     d.smem = encode_smem_of(d.kind, d.P, d.max_blocks, d.out_words_cap);
     if (d.smem > kMaxDynSmem) { *rc_out = X3_ERR_UNSUPPORTED_PARAMS; return cudaSuccess; }
   }
-  // resident CTAs per SM of this kernel at this shared-memory size (cached: the query costs more than the launch)
-  int occ;
-  {
-    std::lock_guard<std::mutex> lk(g_dev_mu);
-    int &slot = ds->occ[d.kind];
-    size_t &slot_smem = ds->occ_smem[d.kind];
-    if (slot == 0 || slot_smem != d.smem) { slot = encode_occupancy(d.kind, d.smem); slot_smem = d.smem; }
-    occ = slot;
+  // one launch of kernel `kind` with its own shared-memory size and grid
+  auto launch_kind = [&](int kind) -> cudaError_t {
+    const size_t smem = encode_smem_of(kind, d.P, d.max_blocks, d.out_words_cap);
+    // resident CTAs per SM of this kernel at this shared-memory size (cached: the query costs more than the launch)
+    int occ;
+    {
+      std::lock_guard<std::mutex> lk(g_dev_mu);
+      int &slot = ds->occ[kind];
+      size_t &slot_smem = ds->occ_smem[kind];
+      if (slot == 0 || slot_smem != smem) { slot = encode_occupancy(kind, smem); slot_smem = smem; }
+      occ = slot;
+    }
+    unsigned long long grid = (unsigned long long)ds->sms * (unsigned)occ;
+    if (kind != kEncKernelGeneric) {  // CTA 0 is the scanner, the others encode
+      if (grid > nf + 1) grid = nf + 1;
+      if (grid < 2) grid = 2;
+    } else if (grid > nf) {
+      grid = nf;
+    }
+    g_launches++;
+    return launch_encode(a, kind, (int)grid, smem, st);
+  };
+  const size_t ws_bytes = encode_ws_bytes(nf);
+  // Parameters::default(): the probe zeroes the workspace and picks between the strip kernel and the block-per-thread
+  // kernel; both are launched, the one not picked returns at once (no host round trip).  A call too small to matter,
+  // or a frame image too large for the block-per-thread kernel, just takes the strip kernel.
+  const bool adaptive = d.kind == kEncKernelStrip && forced_kernel() < 0 && nf >= 64 &&
+                        encode_smem_of(kEncKernelFast, d.P, d.max_blocks, d.out_words_cap) <= kMaxDynSmem;
+  cudaError_t e;
+  if (adaptive) {
+    unsigned int *choice = reinterpret_cast<unsigned int *>(ws + 72);
+    e = launch_encode_probe(d_pcm, n_samples, ws, ws_bytes, choice, st);
+    g_launches++;
+    if (e != cudaSuccess) return e;
+    a.choice = choice;
+    e = launch_kind(kEncKernelStrip);
+    if (e != cudaSuccess) return e;
+    return launch_kind(kEncKernelFast);
   }
-  unsigned long long grid = (unsigned long long)ds->sms * (unsigned)occ;
-  if (d.kind != kEncKernelGeneric) {  // CTA 0 is the scanner, the others encode
-    if (grid > nf + 1) grid = nf + 1;
-    if (grid < 2) grid = 2;
-  } else if (grid > nf) {
-    grid = nf;
-  }
-  e = launch_encode(a, d.kind, (int)grid, d.smem, st);
-  g_launches++;
-  return e;
+  e = cudaMemsetAsync(ws, 0, ws_bytes, st);
+  if (e != cudaSuccess) return e;
+  return launch_kind(d.kind);
 }
 
 }  // namespace
@@ -449,7 +479,7 @@ int x3_encode_device(const int16_t *d_pcm, size_t n_samples, const x3_params *p,
   cudaError_t e = enqueue_encode(d, ds, d_pcm, n_samples, d_out, out_cap, ws, st, &rc);
   tm.stop();
   if (rc) { cudaFreeAsync(ws, st); return rc; }
-  if (e == cudaSuccess) e = cudaMemcpyAsync(host_res, ws, 64, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(host_res, ws, 80, cudaMemcpyDeviceToHost, st);   // results + the probe's choice
 #ifdef X3_ENC_TIMING
   if (e == cudaSuccess) e = cudaMemcpyAsync(host_res + 16, ws + 128 + 8 * (size_t)nf, 256, cudaMemcpyDeviceToHost, st);
 #endif
@@ -457,6 +487,10 @@ int x3_encode_device(const int16_t *d_pcm, size_t n_samples, const x3_params *p,
   cudaFreeAsync(ws, st);
   if (e != cudaSuccess) return cuda_fail(e, "encode_frames_kernel");
   tl_ms[0] = tl_ms[2] = tm.ms();
+  {
+    const unsigned int picked = (unsigned int)(host_res[9] & 0xffffffffull);   // ws + 72: 0 unless the probe ran
+    tl_enc_kernel = picked ? (int)picked : (d.kind == kEncKernelStrip && forced_kernel() == (int)kEncKernelFast ? (int)kEncKernelFast : -2);
+  }
 #ifdef X3_ENC_TIMING
   {
     const char *names[] = {"waitA", "measure", "waitB", "scan2", "pack", "waitD", "or", "waitE", "crc", "waitOff", "copy", "frames",

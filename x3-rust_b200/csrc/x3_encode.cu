@@ -473,6 +473,7 @@ __device__ __forceinline__ void scanner_role(const EncodeArgs &a) {
 // per frame), which turns all shared-memory address arithmetic into immediates; 0 = take them from the arguments.
 template <uint32_t SPF, uint32_t OWC>
 __global__ void __launch_bounds__(NTF, 2) encode_frames_fast_kernel(const __grid_constant__ EncodeArgs a) {
+  if (a.choice && *a.choice != (unsigned)kEncKernelFast) return;   // the probe picked the strip kernel
   if (blockIdx.x == 0) {
     scanner_role(a);
     return;
@@ -1094,6 +1095,7 @@ __device__ __noinline__ uint32_t slow_frame(const EncodeArgs &a, const StripShar
 }
 
 __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __grid_constant__ EncodeArgs a) {
+  if (a.choice && *a.choice != (unsigned)kEncKernelStrip) return;  // the probe picked the block-per-thread kernel
   if (blockIdx.x == 0) {
     scanner_role(a);
     return;
@@ -1330,6 +1332,48 @@ __global__ void __launch_bounds__(NTS, 5) encode_frames_strip_kernel(const __gri
   if (tid < 6 && s_misc[16 + tid]) atomicAdd(a.result + 2 + tid, (unsigned long long)s_misc[16 + tid]);
 }
 
+
+// Workspace zeroing + kernel choice (x3_kernels.h).  CTA 0 zeroes the first 128 bytes (results, ticket, choice), codes
+// the sampled blocks and writes the choice; the other CTAs zero the rest of the workspace.
+__global__ void __launch_bounds__(256) encode_probe_kernel(const int16_t *pcm, unsigned long long n_samples, uint4 *ws,
+                                                           unsigned long long ws_vecs, unsigned int *choice) {
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  if (blockIdx.x != 0) {
+    for (unsigned long long i = 8ull + (unsigned long long)(blockIdx.x - 1u) * 256u + threadIdx.x; i < ws_vecs;
+         i += (unsigned long long)(gridDim.x - 1u) * 256u)
+      ws[i] = z;
+    return;
+  }
+  __shared__ unsigned int s_big, s_all;
+  if (threadIdx.x < 8) ws[threadIdx.x] = z;
+  if (threadIdx.x == 0) { s_big = 0; s_all = 0; }
+  if (gridDim.x == 1)
+    for (unsigned long long i = 8ull + threadIdx.x; i < ws_vecs; i += 256u) ws[i] = z;
+  __syncthreads();
+  const unsigned long long nblocks = n_samples > 1 ? (n_samples - 1) / 20ull : 0ull;   // 20 differences each
+  const unsigned long long take = nblocks < 256ull ? nblocks : 256ull;                 // one block per thread
+  unsigned int big = 0, all = 0;
+  if (threadIdx.x < take) {
+    const int16_t *q = pcm + (unsigned long long)threadIdx.x * (nblocks / take) * 20ull;
+    int v[21];
+#pragma unroll
+    for (int i = 0; i <= 20; i++) v[i] = q[i];     // 21 independent loads: one memory latency
+    int m = 0;
+#pragma unroll
+    for (int i = 1; i <= 20; i++) {
+      const int d = v[i] - v[i - 1], ad = d < 0 ? -d : d;
+      m = ad > m ? ad : m;
+    }
+    all = 1;
+    big = m > 20;   // Parameters::default(): a block whose largest difference exceeds thresholds[2] is BFP / literal
+  }
+  atomicAdd(&s_big, big);
+  atomicAdd(&s_all, all);
+  __syncthreads();
+  if (threadIdx.x == 0)
+    *choice = (s_all && 100u * s_big > kProbeBigPercent * s_all) ? (unsigned)kEncKernelFast : (unsigned)kEncKernelStrip;
+}
+
 }  // namespace
 
 size_t encode_smem_bytes(const CodecParams &P, uint32_t max_blocks, uint32_t out_words_cap) {
@@ -1368,6 +1412,15 @@ cudaError_t launch_encode(const EncodeArgs &a, int kind, int grid, size_t smem, 
     if (e != cudaSuccess) return e;
     encode_frames_generic_kernel<<<grid, NT, smem, stream>>>(a);
   }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_encode_probe(const int16_t *pcm, unsigned long long n_samples, unsigned char *ws, size_t ws_bytes,
+                                unsigned int *choice, cudaStream_t stream) {
+  const unsigned long long vecs = ws_bytes / 16;   // the workspace size is a multiple of 16
+  unsigned grid = 1u + (unsigned)((vecs + 256ull * 16ull - 1ull) / (256ull * 16ull));
+  if (grid > 149u) grid = 149u;
+  encode_probe_kernel<<<grid, 256, 0, stream>>>(pcm, n_samples, reinterpret_cast<uint4 *>(ws), vecs, choice);
   return cudaGetLastError();
 }
 

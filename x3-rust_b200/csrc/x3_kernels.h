@@ -37,6 +37,7 @@ struct EncodeArgs {
   unsigned long long *timing;  // 32 words, only written when built with -DX3_ENC_TIMING
   const uint16_t *crc_tables;  // kCrcBankEntries3 (normal bank, byte-swapped bank, nibble multiply tables)
   int32_t neg_one;             // -1, opaque to the compiler: lets the kernel compute ~x as x*(-1)-1 on the FMA pipe
+  const unsigned int *choice;  // null, or the kernel kind encode_probe_kernel picked: a kernel of another kind returns at once
 };
 
 size_t encode_smem_bytes(const CodecParams &P, uint32_t max_blocks, uint32_t out_words_cap);
@@ -44,6 +45,14 @@ size_t encode_fast_smem_bytes(const CodecParams &P, uint32_t out_words_cap);
 size_t encode_strip_smem_bytes();
 int encode_occupancy(int kind, size_t smem);
 cudaError_t launch_encode(const EncodeArgs &a, int kind, int grid, size_t smem, cudaStream_t stream);
+// Zeroes the encoder workspace [ws, ws + ws_bytes) and picks the kernel for a Parameters::default() input: it codes
+// 256 blocks spread evenly over the input and writes kEncKernelFast to *choice when more than
+// kProbeBigPercent of them are BFP / literal blocks (frames of such input overflow the strip kernel's 8 KiB windows
+// and take its slow paths; the block-per-thread kernel keeps a whole frame image in shared memory), else
+// kEncKernelStrip.
+constexpr unsigned kProbeBigPercent = 20;
+cudaError_t launch_encode_probe(const int16_t *pcm, unsigned long long n_samples, unsigned char *ws, size_t ws_bytes,
+                                unsigned int *choice, cudaStream_t stream);
 
 // One frame of a stream, as found by the frame index (device scan or host walk).
 struct FrameRec {

@@ -414,7 +414,7 @@ int sim_inv_table_check() {
   for (int f = 1; f <= 3; f++) {
     const RiceBlockPar bp = rice_block_par((uint32_t)f);
     const int nbk = (int)inv_nbk((uint32_t)f), level = 1 << (nbk - 1);
-    if (bp.sh != 24u - (uint32_t)nbk || bp.rc != 0u - (158u + (uint32_t)nbk) || bp.tab_off != inv_tab_off((uint32_t)f)) return 10 + f;
+    if (bp.sh != inv_q_shift((uint32_t)f) || bp.rc != 0u - (158u + (uint32_t)nbk) || bp.tab_off != inv_tab_off((uint32_t)f)) return 10 + f;
     uint32_t banks = 0;
     for (int z = 0; z <= 31; z++)
       for (int r = level; r < (1 << nbk); r++)
@@ -433,7 +433,7 @@ int sim_inv_table_check() {
           uint32_t left = 32u;
           left = mad_hi_u32(fb, 512u, left + bp.rc);
           if (left != 32u - (uint32_t)(z + nbk)) return 50 + f;
-          if (valid) banks |= 1u << (((bp.tab_off + Q) >> 2) & 31u);
+          if (valid && z <= 3) banks |= 1u << (((bp.tab_off + Q) >> 2) & 31u);   // the frequent codes
         }
     if (inv_tab_entry((int)bp.tab_off) != kInvBad) return 60 + f;          // an all-zero peek: float 0, Q = 0
     if (banks & banks_used) return 70 + f;

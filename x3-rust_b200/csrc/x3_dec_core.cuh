@@ -358,17 +358,41 @@ X3_HD bool frame_fast_eligible(uint32_t samples, uint32_t payload_len, uintptr_t
 typedef int8_t inv_entry_t;
 constexpr int kInvBad = -128;
 constexpr int kInvExpBias = 158;                    // exponent field of float(t) for a t with bit 31 set
-constexpr int kInvOff1 = 84, kInvOff2 = 288, kInvOff3 = 712;
-constexpr int kInvTabEntries = kInvOff3 + (kInvExpBias + 1) * 8;   // 1984
-X3_HD uint32_t inv_tab_off(uint32_t f) { return f == 1u ? (uint32_t)kInvOff1 : (f == 2u ? (uint32_t)kInvOff2 : (uint32_t)kInvOff3); }
+#ifndef X3_DEC_FIXSHIFT
+#define X3_DEC_FIXSHIFT 0   // 1 was measured: one instruction less per code, bank conflicts between the tables, no change in time
+#endif
 X3_HD uint32_t inv_nbk(uint32_t f) { return f == 1u ? 1u : (f == 2u ? 2u : 4u); }
 X3_HD uint32_t inv_len_of(uint32_t f) { return f == 1u ? 16u : (f == 2u ? 26u : 60u); }   // x3.rs:214,222,250
+#if X3_DEC_FIXSHIFT
+// X3_DEC_FIXSHIFT: every table is indexed by Q = bits >> 20 (exponent and THREE mantissa bits) whatever nbk is, and the
+// mantissa bits a code does not own are don't-cares (its entries are repeated 4 or 2 times).  The shift is then a
+// constant, and shift + table offset become ONE LEA.HI instead of a shift and an add.  The tables are 1272 bytes each
+// and can no longer sit in disjoint banks; their offsets put the entries of the frequent short zero runs (z <= 3 of
+// every table) in different banks.
+constexpr int kInvQShift = 20;
+constexpr int kInvTabLen = (kInvExpBias + 1) * 8;   // 1272
+constexpr int kInvOff1 = 0, kInvOff2 = 1312, kInvOff3 = 2624;   // = 0, 32, 64 mod 128
+constexpr int kInvTabEntries = kInvOff3 + kInvTabLen;
+#else
+constexpr int kInvOff1 = 84, kInvOff2 = 288, kInvOff3 = 712;
+constexpr int kInvTabEntries = kInvOff3 + (kInvExpBias + 1) * 8;   // 1984
+#endif
+X3_HD uint32_t inv_tab_off(uint32_t f) { return f == 1u ? (uint32_t)kInvOff1 : (f == 2u ? (uint32_t)kInvOff2 : (uint32_t)kInvOff3); }
+X3_HD uint32_t inv_q_shift(uint32_t f) {
+#if X3_DEC_FIXSHIFT
+  (void)f;
+  return (uint32_t)kInvQShift;
+#else
+  return 24u - inv_nbk(f);
+#endif
+}
 X3_HD inv_entry_t inv_tab_entry(int j /* 0..kInvTabEntries */) {
   for (uint32_t f = 1; f <= 3; f++) {
-    const int level = 1 << (inv_nbk(f) - 1u);
+    const int per_e = 1 << (23 - (int)inv_q_shift(f));          // entries per exponent value
+    const int level = 1 << (inv_nbk(f) - 1u);                    // of which `level` are distinct codes
     const int Q = j - (int)inv_tab_off(f);
-    if (Q < 0 || Q >= (kInvExpBias + 1) * level) continue;
-    const int z = kInvExpBias - Q / level, i = Q % level + level * z;
+    if (Q < 0 || Q >= (kInvExpBias + 1) * per_e) continue;
+    const int z = kInvExpBias - Q / per_e, i = (Q % per_e) / (per_e / level) + level * z;
     return (z > 31 || i >= (int)inv_len_of(f)) ? (inv_entry_t)kInvBad : (inv_entry_t)unfold((uint32_t)i);
   }
   return (inv_entry_t)kInvBad;   // between the tables
@@ -390,7 +414,7 @@ X3_HD uint32_t f32_rz_bits(uint32_t t) {
 // per-ftype constants of a Rice block, fetched with one 16-byte load
 struct alignas(16) RiceBlockPar {
   uint32_t rc;        // -(158 + nbk): what a code adds to the bits left in the window, apart from its exponent field
-  uint32_t sh;        // 24 - nbk
+  uint32_t sh;        // inv_q_shift: 24 - nbk, or 20 for every table (X3_DEC_FIXSHIFT)
   uint32_t one;       // 1 (opaque to the compiler; entry 0 only)
   uint32_t tab_off;   // entry of Q = 0 in the table bank
 };
@@ -398,7 +422,7 @@ X3_HD RiceBlockPar rice_block_par(uint32_t f) {
   RiceBlockPar p;
   const uint32_t nbk = inv_nbk(f ? f : 1u);
   p.rc = 0u - ((uint32_t)kInvExpBias + nbk);
-  p.sh = 24u - nbk;
+  p.sh = inv_q_shift(f ? f : 1u);
   p.one = 1u;
   p.tab_off = inv_tab_off(f ? f : 1u);
   return p;
@@ -459,11 +483,16 @@ X3_HD uint32_t pack_lo16(uint32_t lo, uint32_t hi) {  // (lo & 0xffff) | (hi << 
 
 // one Rice code of the 64-bit window hi:lo, `left` bits before the window's end (left = 32 - offset): see the table
 // comment.  left only ever decreases; once it is negative the (clamped) shift shows hi again and the block is flagged.
+#if X3_DEC_FIXSHIFT
+#define X3_RICE_LOOKUP(fb) inv_tab[((fb) >> kInvQShift) + bp.tab_off]
+#else
+#define X3_RICE_LOOKUP(fb) tab[(fb) >> bp.sh]
+#endif
 #define X3_RICE_SAMPLE(dv)                                                            \
   {                                                                                   \
     const uint32_t fb = f32_rz_bits(funnel_r(lo, hi, left));                          \
     left = mad_hi_u32(fb, 512u, left + bp.rc);                                        \
-    dv = (int32_t)tab[fb >> bp.sh];                                                   \
+    dv = (int32_t)X3_RICE_LOOKUP(fb);                                                 \
     lw += dv;                                                                         \
   }
 
@@ -497,6 +526,7 @@ X3_HD int decode_frame_fast(Reader &rd, uint32_t payload_len, int16_t *out, uint
       rd.advance(2);
       const RiceBlockPar bp = par[ftype];
       const inv_entry_t *tab = inv_tab + bp.tab_off;
+      (void)tab;
       int32_t dmin = 0, mprev = 0;
       uint32_t lneg = 0, lprev = 0;   // sign bit: some group ran past its 32 bits
       // samples x0..x19; output words (prev,x0) (x1,x2) ... (x17,x18); x19 becomes prev.

@@ -236,6 +236,16 @@ class DeviceCodec:
         return length, list(self.ms_e), list(self.ms_d), [int(v) for v in self.st.samples_by_mode]
 
 
+    def round_trip_async(self, pcm, stream, dec, enc_res, dec_res):
+        """the same round trip through the stream-ordered entry points: only enqueues work, reads nothing back (the
+        decode takes the stream's length from the encode's device-side result)"""
+        rc = self.L.x3_encode_device_async(C.c_void_p(pcm.data_ptr()), pcm.numel(), self.r_ps, C.c_void_p(stream.data_ptr()),
+                                           stream.numel(), C.c_void_p(enc_res.data_ptr()), self.stream)
+        code = self.L.x3_decode_device_async(C.c_void_p(stream.data_ptr()), stream.numel(), C.c_void_p(enc_res.data_ptr()), self.r_ps,
+                                             C.c_void_p(dec.data_ptr()), pcm.numel(), C.c_void_p(dec_res.data_ptr()), self.stream)
+        assert rc == 0 and code == 0, (rc, code)
+
+
 def med(v):
     return sorted(v)[len(v) // 2]
 
@@ -311,6 +321,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the c1 / c4 side measurements of the default N=1 run")
+    ap.add_argument("--sync-api", action="store_true",
+                    help="time the headline through x3_encode_device / x3_decode_device (a host round trip per call) instead of "
+                         "the stream-ordered entry points")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -407,27 +420,107 @@ def main():
             pending = sharding.exchange_sizes_begin(total, dist, device)
         return total, times, stats
 
+    # ---- the headline loop: the stream-ordered entry points (x3_encode_device_async / x3_decode_device_async).  A step
+    # enqueues encode + decode of every batch of the rank and reads nothing back: the decode takes the stream's length
+    # from the encode's device-side result, the shard size for the all-gather is summed on the device.  Results of every
+    # call of the last `keep` steps are kept on the device and checked after the timed region. ----
+    keep = 2
+    res_dev = torch.zeros((keep, len(batches), 2, 8), dtype=torch.int64, device=device)
+    total_dev = torch.zeros(1, dtype=torch.int64, device=device)
+    sizes_dev = [torch.zeros(world, dtype=torch.int64, device=device) for _ in range(2)]
+    handle = None
+
+    def step_async(si):
+        nonlocal handle
+        if handle is not None:       # the exchange of the previous step
+            handle.wait()
+            handle = None
+        if world > 1:
+            total_dev.zero_()
+        for k, b in enumerate(batches):
+            er, dr = res_dev[si % keep, k, 0], res_dev[si % keep, k, 1]
+            codec.round_trip_async(b, stream, dec[:b.numel()], er, dr)
+            if world > 1:
+                total_dev.add_(er[0:1])
+        if world > 1:
+            handle = dist.all_gather_into_tensor(sizes_dev[si & 1], total_dev, async_op=True)
+
+    def check_async(si, stats_ref, total_ref):
+        """every call of step si: all samples back, no flag, no bad frame; sizes and statistics equal the sync API's"""
+        r = res_dev[si % keep].cpu().tolist()
+        tot, st = 0, [0] * 6
+        for k, b in enumerate(batches):
+            er, dr = r[k]
+            assert er[1] == 0 and dr[0] == b.numel() and dr[1] == 0 and dr[3] == -1, (k, er, dr)
+            assert dr[5] == er[0], "the decode must consume the whole stream"
+            tot += er[0]
+            st = [x + y for x, y in zip(st, er[2:8])]
+        assert tot == total_ref and st == stats_ref, (tot, total_ref, st, stats_ref)
+
     for w in range(args.warmup):
-        length, _, stats = step(check=(w == 0))      # parity gate before any number is reported
+        length, _, stats = step(check=(w == 0))      # parity gate before any number is reported (sync API, bit-exact)
+    if pending is not None:
+        shard_sizes, _base = sharding.exchange_sizes_end(pending)
+        pending = None
+    if not args.sync_api:
+        step_async(0)
+        if handle is not None:
+            handle.wait()
+            handle = None
+        torch.cuda.synchronize()
+        check_async(0, stats, length)
+        assert torch.equal(dec[:batches[-1].numel()], batches[-1]), "stream-ordered round trip is not bit-exact"
     barrier()
+
+    # ---- per-kernel times: the sync API's own CUDA events (x3_last_kernel_ms), a few steps outside the headline loop ----
+    enc_t, dec_t, idx_t, crc_t, all_t, alg_b = [], [], [], [], [], []
+
+    def collect(times):
+        for nb, lb, me, md in times:
+            enc_t.append(me[0]); dec_t.append(md[0]); idx_t.append(md[1]); crc_t.append(md[3]); all_t.append(md[2])
+            alg_b.append(2.0 * nb + lb)
+    sync_ms = None
+    if not args.sync_api:
+        ks = max(2, min(args.steps, 5))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(ks):
+            length, times, stats = step()
+            collect(times)
+        e1.record()
+        barrier()
+        if pending is not None:
+            shard_sizes, _ = sharding.exchange_sizes_end(pending)
+            pending = None
+        sync_ms = e0.elapsed_time(e1) / ks
 
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = dev.kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    enc_t, dec_t, idx_t, crc_t, all_t, alg_b = [], [], [], [], [], []
     barrier()
     e0.record()
-    for _ in range(args.steps):
-        length, times, stats = step()
-        for nb, lb, me, md in times:
-            enc_t.append(me[0]); dec_t.append(md[0]); idx_t.append(md[1]); crc_t.append(md[3]); all_t.append(md[2])
-            alg_b.append(2.0 * nb + lb)
+    for si in range(args.steps):
+        if args.sync_api:
+            length, times, stats = step()
+            collect(times)
+        else:
+            step_async(si)
     e1.record()
     barrier()
     if pending is not None:
         shard_sizes, _ = sharding.exchange_sizes_end(pending)
         pending = None
+    if handle is not None:
+        handle.wait()
+        handle = None
+        torch.cuda.synchronize()
+    if not args.sync_api:
+        for si in range(max(0, args.steps - keep), args.steps):
+            check_async(si, stats, length)
+        if world > 1:
+            shard_sizes = [int(v) for v in sizes_dev[(args.steps - 1) & 1].tolist()]
     launches = dev.kernel_launch_count() - launches0
     dt_ms = e0.elapsed_time(e1) / args.steps
     t = torch.tensor([dt_ms], dtype=torch.float64, device=device)
@@ -558,12 +651,19 @@ def main():
         "config": {"workload": workload, "params": "Parameters::default()", "samples_per_gpu": n, "samples_total": n_total,
                    "batches_per_gpu": len(batches), "compressed_ratio": bytes_total / (2.0 * n_total),
                    "l2": "inputs larger than L2 (2.76 GB PCM per encode call)",
-                   "step": "x3_encode_device then x3_decode_device on device-resident buffers, for every batch of the rank"},
+                   "step": ("x3_encode_device then x3_decode_device on device-resident buffers, for every batch of the rank (a host "
+                            "round trip per call)" if args.sync_api else
+                            "x3_encode_device_async then x3_decode_device_async on device-resident buffers, for every batch of the "
+                            "rank: stream-ordered, the decode reads the stream's length from the encode's device-side result; "
+                            "every call's result is checked after the timed region")},
         "gb_per_s_pcm": 2.0 * n_total / (dt_ms * 1e-3) / 1e9,
         "encode_msamples_s": kernels["encode_frames_kernel"]["msamples_s"] * world,
         "decode_msamples_s": nb0 / med(all_t) / 1e3 * world,   # whole decode section: index, then decode || crc
         "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": int(launches), "clocks": sampler.summary(),
+        "sync_api": None if sync_ms is None else {
+            "ms_per_step": sync_ms, "note": "the same steps through x3_encode_device / x3_decode_device (each call reads its "
+            "results back and synchronises); the per-kernel times in `kernels` and `roofline` are that API's own CUDA events"},
         "mode_stats": stats, "shard_sizes": shard_sizes if world > 1 else [int(length)],
     }
     if workloads is not None:

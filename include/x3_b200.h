@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define X3_B200_ABI_VERSION 2
+#define X3_B200_ABI_VERSION 3
 
 /* ---- error codes ------------------------------------------------------------------------- */
 enum {
@@ -133,6 +133,32 @@ int x3_decode_host(const uint8_t *frames, size_t len, const x3_params *p, int16_
                    size_t pcm_cap, size_t *n_out, x3_decode_result *res);
 int x3_decode_device(const uint8_t *d_frames, size_t len, const x3_params *p, int16_t *d_pcm,
                      size_t pcm_cap, size_t *n_out, x3_decode_result *res, void *cuda_stream);
+
+/* ---- stream-ordered variants (ABI v3): nothing is read back, nothing synchronises ------------ */
+/* For callers that keep the data on the device and chain calls on one CUDA stream (encode -> decode, or many
+ * batches back to back): the calls only enqueue work.  Results stay on the device in an x3_device_result the
+ * caller owns (device memory, 8-byte aligned); it is valid once `cuda_stream` has reached the end of the call.
+ * The decode takes the stream's length from device memory (`d_len`, e.g. &encode_result->value) -- `len_cap` is an
+ * upper bound used to size the workspace -- so an encode and the decode of its output need no host round trip.
+ * These entry points do not fall back: where x3_decode_device would retry with a larger frame table or walk the
+ * stream on the host (flags != 0), they report the flag and the caller repeats the call with x3_decode_device.
+ *   encode: value = bytes written, flags bit 0 = output capacity exceeded (nothing usable), detail[0..6) =
+ *           x3_stats.samples_by_mode.
+ *   decode: value = samples written (all frames before the first bad one), flags bit 0 = the frame table could not
+ *           be proven to be the reference's walk, bit 1 = a capacity (frames per tile / table size) was exceeded,
+ *           detail[0] = frames decoded, [1] = first bad frame (or ~0), [2] = its kDec* status as a signed value
+ *           (-11 payload CRC, -9 payload length, -2 / -13 in-frame decode errors, -15 output capacity), [3] = bytes
+ *           of the stream the walk consumed. */
+typedef struct x3_device_result {
+  uint64_t value;
+  uint64_t flags;
+  uint64_t detail[6];
+} x3_device_result;
+int x3_encode_device_async(const int16_t *d_pcm, size_t n_samples, const x3_params *p, uint8_t *d_out,
+                           size_t out_cap, x3_device_result *d_res, void *cuda_stream);
+int x3_decode_device_async(const uint8_t *d_frames, size_t len_cap, const uint64_t *d_len, const x3_params *p,
+                           int16_t *d_pcm, size_t pcm_cap, x3_device_result *d_res, void *cuda_stream);
+
 /* decoder::decode_frame (decoder.rs:36-58): one payload (no header), `samples` from its header.  Like the
  * reference's function it has no 24 KiB payload limit (that one belongs to X3aReader, decodefile.rs:118-121):
  * any payload below Frame::MAX_LENGTH is taken. */

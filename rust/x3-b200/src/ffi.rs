@@ -35,6 +35,9 @@ pub struct x3_decode_result {
     pub used_host_walk: i32,
 }
 
+#[repr(C)]
+pub struct x3_device_result { pub value: u64, pub flags: u64, pub detail: [u64; 6] }
+
 extern "C" {
     pub fn x3_abi_version() -> c_int;
     pub fn x3_params_default(p: *mut x3_params) -> c_int;
@@ -67,4 +70,9 @@ extern "C" {
     pub fn x3_kernel_launch_count() -> u64;
     pub fn x3_last_kernel_ms(ms: *mut f32) -> c_int;
     pub fn x3_last_encode_kernel() -> c_int;
+    // stream-ordered variants (ABI v3): results stay on the device in an x3_device_result
+    pub fn x3_encode_device_async(d_pcm: *const i16, n: usize, p: *const x3_params, d_out: *mut u8, cap: usize,
+                                  d_res: *mut x3_device_result, stream: *mut c_void) -> c_int;
+    pub fn x3_decode_device_async(d_frames: *const u8, len_cap: usize, d_len: *const u64, p: *const x3_params,
+                                  d_pcm: *mut i16, cap: usize, d_res: *mut x3_device_result, stream: *mut c_void) -> c_int;
 }

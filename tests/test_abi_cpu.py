@@ -23,7 +23,7 @@ def test_header_symbols_exported(built):
     assert declared == set(built._lib.SYMBOLS), declared ^ set(built._lib.SYMBOLS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.x3_abi_version() == 2
+    assert lib.x3_abi_version() == 3
 
 
 def test_params_and_bound(built, oracle):

@@ -582,3 +582,70 @@ def test_forced_encode_kernels_match_oracle(oracle, kernel, tmp_path):
     env = dict(os.environ, X3_ENC_KERNEL=kernel)
     r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_stream_ordered_api_matches_sync(pkg, dev, oracle):
+    """x3_encode_device_async / x3_decode_device_async: an encode and the decode of its output chained on one stream
+    with no host round trip (the decode reads the stream's length from the encode's device-side result) give the
+    sync API's bytes, samples and verdicts -- on clean input, with a flipped payload bit, a damaged header, a stream
+    of small frames (capacity flag) and a too-small output buffer."""
+    import torch
+    p = pkg.x3.Parameters.default()
+    for kind, seed, n in ((2, 0x58330002, 3000000 + 1234), (4, 0x58330004, 1500000), (2, 0x58330002, 777)):
+        pcm = dev.synth(kind, seed, 384000, 0, n)
+        ref_out, ref_len, ref_stats = dev.encode_tensor(pcm, p)
+        out = torch.zeros(ref_out.numel(), dtype=torch.uint8, device="cuda")
+        enc_res = torch.full((8,), -1, dtype=torch.int64, device="cuda")
+        dec_res = torch.full((8,), -1, dtype=torch.int64, device="cuda")
+        dec = torch.zeros(n, dtype=torch.int16, device="cuda")
+        dev.encode_tensor_async(pcm, out, enc_res, p)
+        dev.decode_tensor_async(out, enc_res[0:1], dec, dec_res, p)
+        torch.cuda.synchronize()
+        er, dr = enc_res.tolist(), dec_res.tolist()
+        assert er[0] == ref_len and er[1] == 0 and er[2:8] == ref_stats
+        assert torch.equal(out[:ref_len], ref_out[:ref_len])
+        assert dr[0] == n and dr[1] == 0 and dr[2] == (n + 9999) // 10000 and dr[3] == -1 and dr[5] == ref_len
+        assert torch.equal(dec, pcm)
+    # a flipped payload bit in frame 3: everything before it is delivered, the verdict is the payload CRC
+    n = 100000
+    pcm = dev.synth(2, 0x58330002, 384000, 0, n)
+    out, length, _ = dev.encode_tensor(pcm, p)
+    host = out[:length].cpu().numpy()
+    pos = 0
+    for _ in range(3):
+        pos += 20 + ((int(host[pos + 6]) << 8) | int(host[pos + 7]))
+    bad = out.clone()
+    bad[pos + 20 + 100] ^= 4
+    length_dev = torch.tensor([length], dtype=torch.int64, device="cuda")
+    dec = torch.zeros(n, dtype=torch.int16, device="cuda")
+    dev.decode_tensor_async(bad, length_dev, dec, dec_res, p)
+    torch.cuda.synchronize()
+    dr = dec_res.tolist()
+    _, ns, res, code = dev.decode_tensor(bad, length, p, max_samples=n)
+    assert (dr[0], dr[1], dr[2], dr[3], dr[4]) == (ns, 0, res.frames, 3, -11) and res.first_bad_frame == 3
+    assert torch.equal(dec[:ns], pcm[:ns])
+    # a damaged header: the table cannot be proven, the flag says "use x3_decode_device"
+    bad = out.clone()
+    bad[pos + 1] ^= 1
+    dev.decode_tensor_async(bad, length_dev, dec, dec_res, p)
+    torch.cuda.synchronize()
+    assert dec_res[1].item() & 1
+    # frames too small for the hop index: capacity flag
+    small = pkg.x3.Parameters(20, 1, (0, 1, 3), (3, 8, 20))
+    pcm2 = dev.synth(2, 0x58330002, 384000, 0, 400000)
+    out2, len2, _ = dev.encode_tensor(pcm2, small)
+    dev.decode_tensor_async(out2, torch.tensor([len2], dtype=torch.int64, device="cuda"),
+                            torch.zeros(400000, dtype=torch.int16, device="cuda"), dec_res, small)
+    torch.cuda.synchronize()
+    assert dec_res[1].item() & 2
+    # output too small: the frames that fit are delivered, the first that does not is reported (-15)
+    dec_small = torch.zeros(25000, dtype=torch.int16, device="cuda")
+    dev.decode_tensor_async(out, length_dev, dec_small, dec_res, p)
+    torch.cuda.synchronize()
+    dr = dec_res.tolist()
+    assert dr[0] == 20000 and dr[2] == 2 and dr[3] == 2 and dr[4] == -15 and torch.equal(dec_small[:20000], pcm[:20000])
+    # encode output too small: flag, nothing usable
+    tiny = torch.zeros(1000, dtype=torch.uint8, device="cuda")
+    dev.encode_tensor_async(pcm, tiny, enc_res, p)
+    torch.cuda.synchronize()
+    assert enc_res[1].item() & 1

@@ -61,6 +61,9 @@ SYMBOLS = {
     "x3_kernel_launch_count": (C.c_uint64, []),
     "x3_last_kernel_ms": (C.c_int, [_P(C.c_float * 4)]),
     "x3_last_encode_kernel": (C.c_int, []),
+    "x3_encode_device_async": (C.c_int, [C.c_void_p, C.c_size_t, _P(x3_params), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "x3_decode_device_async": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, _P(x3_params), C.c_void_p, C.c_size_t, C.c_void_p,
+                                         C.c_void_p]),
 }
 
 _lib = None

@@ -379,7 +379,7 @@ thread_local HostPipe tl_pipe;
 
 // zero the workspace and launch the encode kernel for n_samples (> 0) on `st`; no synchronisation
 cudaError_t enqueue_encode(Derived d, DeviceState *ds, const int16_t *d_pcm, size_t n_samples, uint8_t *d_out, size_t out_cap,
-                           unsigned char *ws, cudaStream_t st, int *rc_out) {
+                           unsigned char *ws, cudaStream_t st, int *rc_out, unsigned long long *result_dev = nullptr) {
   *rc_out = X3_OK;
   const unsigned long long nf = (n_samples + d.P.spf - 1) / d.P.spf;
   EncodeArgs a;
@@ -391,7 +391,7 @@ cudaError_t enqueue_encode(Derived d, DeviceState *ds, const int16_t *d_pcm, siz
   a.n_frames = (uint32_t)nf;
   a.max_blocks = d.max_blocks;
   a.out_words_cap = d.out_words_cap;
-  a.result = reinterpret_cast<unsigned long long *>(ws);        // 8 words
+  a.result = result_dev ? result_dev : reinterpret_cast<unsigned long long *>(ws);        // 8 words (the caller's, zeroed by the caller, in the stream-ordered API)
   a.ticket = reinterpret_cast<unsigned int *>(ws + 64);
   a.status = reinterpret_cast<unsigned long long *>(ws + 128);
   a.timing = reinterpret_cast<unsigned long long *>(ws + 128 + 8 * (size_t)nf);
@@ -843,6 +843,7 @@ int decode_device_attempt(const uint8_t *d_frames, size_t len, const x3_params *
   sa.crc_tables = ds->crc_dev;
   sa.n_tiles = n_tiles;
   sa.tile_bytes = tile_bytes;
+  sa.len_dev = nullptr;
 
   DecodeArgs da;
   da.stream = d_frames;
@@ -859,6 +860,7 @@ int decode_device_attempt(const uint8_t *d_frames, size_t len, const x3_params *
   da.max_payload = tl_max_payload;
   da.result = reinterpret_cast<unsigned long long *>(ws + o_dres);
   da.crc_tables = ds->crc_dev;
+  da.len_dev = nullptr;
 
   cudaStream_t s2 = fork_stream();
   if (!s2) s2 = st;  // no second stream: the two kernels simply run one after the other
@@ -1175,6 +1177,123 @@ int x3_decode_frame_host(const uint8_t *payload, size_t payload_len, const x3_pa
   tl_max_payload = kReadBufferSize;
   if (rc == X3_OK && r.frame_errors) return r.first_bad_code;  // decode_frame itself returns the Err
   return rc;
+}
+
+
+// ---- stream-ordered entry points: nothing is read back, nothing synchronises -------------------------------------
+int x3_encode_device_async(const int16_t *d_pcm, size_t n_samples, const x3_params *p, uint8_t *d_out, size_t out_cap,
+                           x3_device_result *d_res, void *cuda_stream) {
+  Derived d;
+  int rc = derive(p, &d);
+  if (rc) return rc;
+  if (!d_res || (n_samples && (!d_pcm || !d_out))) return X3_ERR_INVALID_ARGUMENT;
+  if (((uintptr_t)d_pcm & 1u) != 0 || ((uintptr_t)d_res & 7u) != 0) return X3_ERR_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  CU(cudaMemsetAsync(d_res, 0, sizeof *d_res, st));
+  if (n_samples == 0) return X3_OK;
+  DeviceState *ds;
+  if ((rc = device_state(&ds))) return rc;
+  const unsigned long long nf = (n_samples + d.P.spf - 1) / d.P.spf;
+  if (nf > 0xfffffff0ull) return X3_ERR_UNSUPPORTED_PARAMS;
+  unsigned char *ws = nullptr;
+  CU(cudaMallocAsync(&ws, encode_ws_bytes(nf), st));
+  cudaError_t e = enqueue_encode(d, ds, d_pcm, n_samples, d_out, out_cap, ws, st, &rc, reinterpret_cast<unsigned long long *>(d_res));
+  cudaFreeAsync(ws, st);   // stream-ordered: after the kernels
+  if (rc) return rc;
+  if (e != cudaSuccess) return cuda_fail(e, "encode_frames_kernel");
+  return X3_OK;
+}
+
+int x3_decode_device_async(const uint8_t *d_frames, size_t len_cap, const uint64_t *d_len, const x3_params *p, int16_t *d_pcm,
+                           size_t pcm_cap, x3_device_result *d_res, void *cuda_stream) {
+  Derived d;
+  int rc = derive(p, &d);
+  if (rc == X3_ERR_UNSUPPORTED_PARAMS) {
+    if (!p || p->block_len == 0) return X3_ERR_INVALID_ARGUMENT;
+    d.P.block_len = p->block_len;
+    d.P.spf = 0;
+    for (int k = 0; k < 3; k++) { d.P.codes[k] = p->codes[k]; d.P.thresholds[k] = p->thresholds[k]; }
+    rc = X3_OK;
+  }
+  if (rc) return rc;
+  if (!d_res || !d_frames || (!d_pcm && pcm_cap)) return X3_ERR_INVALID_ARGUMENT;
+  if (((uintptr_t)d_pcm & 1u) != 0 || ((uintptr_t)d_res & 7u) != 0 || ((uintptr_t)d_len & 7u) != 0) return X3_ERR_INVALID_ARGUMENT;
+  if (((uintptr_t)d_frames & 15u) != 0) return X3_ERR_INVALID_ARGUMENT;   // the device index needs a 16-byte aligned base
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  DeviceState *ds;
+  if ((rc = device_state(&ds))) return rc;
+  const uint32_t tile_bytes = hop_tile_bytes();
+  unsigned long long max_frames = len_cap / 256 + 4096;
+  const unsigned long long most = len_cap / 22 + 1;
+  if (max_frames > most) max_frames = most;
+  const uint32_t n_tiles = (uint32_t)((len_cap + tile_bytes - 1) / tile_bytes);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t o_res = take(64), o_dres = take(64), o_tick = take(64);
+  const size_t zero_bytes = off;
+  const size_t o_tiles = take(8 * (size_t)(n_tiles ? n_tiles : 1)), o_trecs = take(8 * (size_t)(n_tiles ? n_tiles : 1));
+  const size_t o_frames = take(sizeof(FrameRec) * max_frames), o_fstat = take(sizeof(int) * max_frames);
+  const size_t o_cstat = take(sizeof(int) * max_frames);
+  const size_t o_recs = take(sizeof(FrameRec) * max_frames);
+  unsigned char *ws = nullptr;
+  CU(cudaMallocAsync(&ws, off, st));
+  cudaError_t e = cudaMemsetAsync(ws, 0, zero_bytes, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(ws + o_dres, 0xff, 8, st);
+  auto fail = [&](cudaError_t ee, const char *what) { cudaFreeAsync(ws, st); return cuda_fail(ee, what); };
+  if (e != cudaSuccess) return fail(e, "cudaMemsetAsync");
+  ScanArgs sa;
+  sa.stream = d_frames;
+  sa.stream_len = len_cap;
+  sa.frames = reinterpret_cast<FrameRec *>(ws + o_frames);
+  sa.max_frames = max_frames;
+  sa.recs = reinterpret_cast<FrameRec *>(ws + o_recs);
+  sa.tile_status = reinterpret_cast<unsigned long long *>(ws + o_tiles);
+  sa.ticket = reinterpret_cast<unsigned int *>(ws + o_tick);
+  sa.rec_cursor = reinterpret_cast<unsigned long long *>(ws + o_tick + 8);
+  sa.tile_recs = reinterpret_cast<unsigned long long *>(ws + o_trecs);
+  sa.result = reinterpret_cast<unsigned long long *>(ws + o_res);
+  sa.crc_tables = ds->crc_dev;
+  sa.n_tiles = n_tiles;
+  sa.tile_bytes = tile_bytes;
+  sa.len_dev = reinterpret_cast<const unsigned long long *>(d_len);
+  DecodeArgs da;
+  da.stream = d_frames;
+  da.stream_len = len_cap;
+  da.pcm = d_pcm;
+  da.pcm_cap = pcm_cap;
+  da.P = d.P;
+  da.frames = sa.frames;
+  da.n_frames = sa.result + 4;
+  da.max_frames = max_frames;
+  da.frame_status = reinterpret_cast<int *>(ws + o_fstat);
+  da.crc_status = reinterpret_cast<int *>(ws + o_cstat);
+  da.one = 1u;
+  da.max_payload = kReadBufferSize;
+  da.result = reinterpret_cast<unsigned long long *>(ws + o_dres);
+  da.crc_tables = ds->crc_dev;
+  da.len_dev = sa.len_dev;
+  e = launch_scan(sa, true, st);
+  if (e == cudaSuccess) e = launch_chain_check(sa, st);
+  g_launches += 4;
+  if (e != cudaSuccess) return fail(e, "hop_index_kernel");
+  cudaStream_t s2 = fork_stream();
+  if (!s2) s2 = st;
+  if (s2 != st) {
+    e = cudaEventRecord(tl_fork.fork, st);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s2, tl_fork.fork, 0);
+  }
+  if (e == cudaSuccess) e = launch_decode(da, max_frames, st);
+  if (e == cudaSuccess) e = launch_crc(da, max_frames, s2);
+  g_launches += 2;
+  if (e == cudaSuccess && s2 != st) {
+    e = cudaEventRecord(tl_fork.join, s2);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, tl_fork.join, 0);
+  }
+  if (e == cudaSuccess) e = launch_decode_finalize(sa, da, reinterpret_cast<unsigned long long *>(d_res), st);
+  g_launches++;
+  if (e != cudaSuccess) return fail(e, "decode kernels");
+  cudaFreeAsync(ws, st);
+  return X3_OK;
 }
 
 int x3_synth_device(int kind, uint32_t seed, uint32_t fs, uint64_t n0, uint64_t count, int16_t *d_out,

@@ -85,7 +85,9 @@ __device__ __noinline__ void examine_piece(const ScanArgs &a, const uint16_t *s_
   }
 }
 
-__global__ void __launch_bounds__(kScanThreads) scan_headers_kernel(const ScanArgs a) {
+__global__ void __launch_bounds__(kScanThreads) scan_headers_kernel(const ScanArgs a_in) {
+  ScanArgs a = a_in;
+  if (a.len_dev) a.stream_len = *a.len_dev < a.stream_len ? *a.len_dev : a.stream_len;   // stream-ordered API: the length lies on the device
   __shared__ uint16_t s_T[512];  // T_0, T_1 of the CRC bank are enough for halfword updates
   __shared__ Cand s_cand[kScanCap];
   __shared__ uint32_t s_rank[kScanCap];
@@ -102,7 +104,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_headers_kernel(const ScanAr
     const uint32_t tile = s_tile;
     if (tile >= a.n_tiles) break;
     const unsigned long long t0 = (unsigned long long)tile * a.tile_bytes;
-    const unsigned long long t1 = t0 + a.tile_bytes < a.stream_len ? t0 + a.tile_bytes : a.stream_len;
+    const unsigned long long t1 = t0 >= a.stream_len ? t0 : (t0 + a.tile_bytes < a.stream_len ? t0 + a.tile_bytes : a.stream_len);
 
     // ---- candidates: halfword 'x','3' at an even offset with a valid header behind it ----
     // Whole 16-byte pieces, four independent loads in flight per thread; key hits are rare and handled out of line.
@@ -211,7 +213,9 @@ __device__ __noinline__ unsigned long long first_header_in_piece(const ScanArgs 
 #ifndef X3_HOP_MINBLOCKS
 #define X3_HOP_MINBLOCKS 6
 #endif
-__global__ void __launch_bounds__(kHopThreads, X3_HOP_MINBLOCKS) hop_index_kernel(const ScanArgs a) {
+__global__ void __launch_bounds__(kHopThreads, X3_HOP_MINBLOCKS) hop_index_kernel(const ScanArgs a_in) {
+  ScanArgs a = a_in;
+  if (a.len_dev) a.stream_len = *a.len_dev < a.stream_len ? *a.len_dev : a.stream_len;   // stream-ordered API: the length lies on the device
   __shared__ uint16_t s_T[512];
   __shared__ unsigned long long s_pos[kHopWarps][kHopCap];
   const int tid = threadIdx.x;
@@ -222,7 +226,7 @@ __global__ void __launch_bounds__(kHopThreads, X3_HOP_MINBLOCKS) hop_index_kerne
   const unsigned long long none = ~0ull;
   for (uint32_t tile = blockIdx.x * kHopWarps + wid; tile < a.n_tiles; tile += warps) {
     const unsigned long long t0 = (unsigned long long)tile * a.tile_bytes;
-    const unsigned long long t1 = t0 + a.tile_bytes < a.stream_len ? t0 + a.tile_bytes : a.stream_len;
+    const unsigned long long t1 = t0 >= a.stream_len ? t0 : (t0 + a.tile_bytes < a.stream_len ? t0 + a.tile_bytes : a.stream_len);
     const unsigned long long t1v = t0 + ((t1 - t0) & ~15ull);  // a header does not fit in a shorter tail piece
 
     // ---- the tile's first header: 2 KiB per step, four 16-byte loads in flight per lane ----
@@ -373,7 +377,9 @@ __global__ void __launch_bounds__(256) place_frames_kernel(const ScanArgs a) {
 // The table is the reference's walk iff it starts at 0, every frame ends where the next begins, and
 // nothing but a short tail (<= 20 bytes, decodefile.rs:107-109) or a truncated final frame
 // (decodefile.rs:114-116) follows.
-__global__ void check_chain_kernel(const ScanArgs a) {
+__global__ void check_chain_kernel(const ScanArgs a_in) {
+  ScanArgs a = a_in;
+  if (a.len_dev) a.stream_len = *a.len_dev < a.stream_len ? *a.len_dev : a.stream_len;   // stream-ordered API: the length lies on the device
   const unsigned long long n = a.result[0];
   const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
@@ -465,7 +471,9 @@ struct CrcRingSource {
     issue_one();   // block b + 7 goes to the slot of block b - 1, whose words were consumed before this call
   }
 };
-__global__ void __launch_bounds__(X3_CRC_THREADS) crc_frames_kernel(const DecodeArgs a) {
+__global__ void __launch_bounds__(X3_CRC_THREADS) crc_frames_kernel(const DecodeArgs a_in) {
+  DecodeArgs a = a_in;
+  if (a.len_dev) a.stream_len = *a.len_dev < a.stream_len ? *a.len_dev : a.stream_len;
   __shared__ uint16_t s_T[256];  // byte table, for payloads at odd addresses only
   __shared__ __align__(16) unsigned char s_ring[X3_CRC_THREADS * kCrcRowBytes];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s_T[i] = a.crc_tables[i];
@@ -500,7 +508,9 @@ __global__ void __launch_bounds__(X3_CRC_THREADS) crc_frames_kernel(const Decode
 }
 #else
 // (128 or 64 threads per CTA -- more CTAs beside the decode kernel -- were measured: the pair finishes later)
-__global__ void __launch_bounds__(X3_CRC_THREADS) crc_frames_kernel(const DecodeArgs a) {
+__global__ void __launch_bounds__(X3_CRC_THREADS) crc_frames_kernel(const DecodeArgs a_in) {
+  DecodeArgs a = a_in;
+  if (a.len_dev) a.stream_len = *a.len_dev < a.stream_len ? *a.len_dev : a.stream_len;
   __shared__ uint16_t s_T[kCrcTableEntries];
   for (int i = threadIdx.x; i < kCrcTableEntries; i += blockDim.x) s_T[i] = a.crc_tables[i];
   __syncthreads();
@@ -686,7 +696,9 @@ struct RingReader {
   __device__ __forceinline__ uint32_t bits_used() const { return pos - pos0; }
 };
 
-__global__ void __launch_bounds__(kDecThreads, X3_DEC_MINBLOCKS) decode_frames_kernel(const DecodeArgs a) {
+__global__ void __launch_bounds__(kDecThreads, X3_DEC_MINBLOCKS) decode_frames_kernel(const DecodeArgs a_in) {
+  DecodeArgs a = a_in;
+  if (a.len_dev) a.stream_len = *a.len_dev < a.stream_len ? *a.len_dev : a.stream_len;   // stream-ordered API: the length lies on the device
   __shared__ __align__(16) uint32_t s_ring[kDecThreads * kRingWords];
   __shared__ __align__(16) uint32_t s_stage[kDecThreads * kStageWords];  // [word][thread]
   __shared__ __align__(16) inv_entry_t s_inv[kInvTabEntries];
@@ -737,6 +749,29 @@ __global__ void __launch_bounds__(kDecThreads, X3_DEC_MINBLOCKS) decode_frames_k
   }
 }
 
+
+// Stream-ordered API: the caller's 8 words (x3_device_result).  One thread.
+__global__ void decode_finalize_kernel(const ScanArgs sa, const DecodeArgs da, unsigned long long *out) {
+  const unsigned long long flags = sa.result[2], n = sa.result[4] < da.max_frames ? sa.result[4] : da.max_frames;
+  const unsigned long long first_bad = da.result[0];
+  unsigned long long samples = sa.result[5], frames = n;
+  long long code = 0;
+  if (first_bad < n) {
+    const int cs = da.crc_status[first_bad], fs = da.frame_status[first_bad];
+    code = cs != kDecOk ? cs : fs;   // the reference checks the payload CRC before it decodes (decodefile.rs:93-103)
+    samples = da.frames[first_bad].out_off;
+    frames = first_bad;
+  }
+  out[0] = samples;
+  out[1] = flags;
+  out[2] = frames;
+  out[3] = first_bad < n ? first_bad : ~0ull;
+  out[4] = (unsigned long long)code;
+  out[5] = sa.result[6];   // bytes the walk consumed
+  out[6] = 0;
+  out[7] = 0;
+}
+
 }  // namespace
 
 cudaError_t launch_scan(const ScanArgs &a, bool hop, cudaStream_t stream) {
@@ -767,6 +802,11 @@ cudaError_t launch_chain_check(const ScanArgs &a, cudaStream_t stream) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   check_chain_kernel<<<sms * 4, 256, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_decode_finalize(const ScanArgs &sa, const DecodeArgs &da, unsigned long long *out8, cudaStream_t stream) {
+  decode_finalize_kernel<<<1, 1, 0, stream>>>(sa, da, out8);
   return cudaGetLastError();
 }
 

@@ -81,6 +81,8 @@ struct DecodeArgs {
   uint32_t max_payload;                // X3_READ_BUFFER_SIZE for a stream (decodefile.rs:118-121); no such limit for
                                        // decoder::decode_frame on its own
   const uint16_t *crc_tables;
+  const unsigned long long *len_dev;   // null, or where the stream's length lies on the device (stream-ordered API):
+                                       // read by the kernels in place of stream_len, which is then only an upper bound
 };
 
 cudaError_t launch_crc(const DecodeArgs &a, unsigned long long n_frames_hint, cudaStream_t stream);
@@ -101,12 +103,15 @@ struct ScanArgs {
   const uint16_t *crc_tables;
   uint32_t n_tiles;
   uint32_t tile_bytes;              // kScanTileBytes, or kScanTileBytesSmall on the retry (multiple of 16)
+  const unsigned long long *len_dev;   // see DecodeArgs
 };
 constexpr uint32_t kScanTileBytes = 128 * 1024;
 constexpr uint32_t kScanTileBytesSmall = 16 * 1024;   // >= 22 bytes per frame: at most 745 frames per tile, under the cap
 constexpr uint32_t kHopTileBytes = 64 * 1024;         // hop index: one warp per tile, at most 64 frames in a tile
 cudaError_t launch_scan(const ScanArgs &a, bool hop, cudaStream_t stream);  // hop: follow the headers instead of reading every byte
 cudaError_t launch_chain_check(const ScanArgs &a, cudaStream_t stream);
+// Stream-ordered API: fold the index's and the kernels' verdicts into the caller's 8-word result (x3_device_result).
+cudaError_t launch_decode_finalize(const ScanArgs &sa, const DecodeArgs &da, unsigned long long *out8, cudaStream_t stream);
 
 cudaError_t launch_synth(int kind, uint32_t seed, uint32_t fs, unsigned long long n0, unsigned long long count,
                          int16_t *out, cudaStream_t stream);

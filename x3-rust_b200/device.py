@@ -48,6 +48,32 @@ def encode_tensor(pcm, params=None, out=None):
     return out, out_len.value, [int(v) for v in st.samples_by_mode]
 
 
+def encode_tensor_async(pcm, out, result, params=None):
+    """Stream-ordered encode (x3_encode_device_async): only enqueues work on the current stream.  `result` is an int64
+    CUDA tensor of 8 words (x3_device_result: [0] bytes written, [1] flags, [2..8) samples by mode)."""
+    params = params or x3.Parameters.default()
+    assert pcm.is_cuda and pcm.dtype == torch.int16 and pcm.is_contiguous()
+    assert result.is_cuda and result.dtype == torch.int64 and result.numel() >= 8 and out.dtype == torch.uint8
+    ps = params.c_struct()
+    with _on_device(pcm.device):
+        error.check(_lib.lib().x3_encode_device_async(C.c_void_p(pcm.data_ptr()), pcm.numel(), C.byref(ps), C.c_void_p(out.data_ptr()),
+                                                     out.numel(), C.c_void_p(result.data_ptr()), _stream_ptr()))
+
+
+def decode_tensor_async(frames, length_dev, out, result, params=None):
+    """Stream-ordered decode (x3_decode_device_async): the stream's length is read from device memory (`length_dev`: an
+    int64 CUDA tensor, e.g. the encode's result[0:1]); frames.numel() is the upper bound.  `result` as above:
+    [0] samples written, [1] flags, [2] frames, [3] first bad frame or -1, [4] its status, [5] bytes consumed."""
+    params = params or x3.Parameters.default()
+    assert frames.is_cuda and frames.dtype == torch.uint8 and frames.is_contiguous() and out.dtype == torch.int16
+    assert length_dev.is_cuda and length_dev.dtype == torch.int64 and result.is_cuda and result.dtype == torch.int64
+    ps = params.c_struct()
+    with _on_device(frames.device):
+        error.check(_lib.lib().x3_decode_device_async(C.c_void_p(frames.data_ptr()), frames.numel(), C.c_void_p(length_dev.data_ptr()),
+                                                     C.byref(ps), C.c_void_p(out.data_ptr()), out.numel(),
+                                                     C.c_void_p(result.data_ptr()), _stream_ptr()))
+
+
 def decode_tensor(frames, length, params=None, out=None, max_samples=None):
     """uint8 CUDA tensor with a frame stream of `length` bytes -> (int16 CUDA tensor, n_samples, result, code)."""
     params = params or x3.Parameters.default()

@@ -876,13 +876,22 @@ int decode_device_attempt(const uint8_t *d_frames, size_t len, const x3_params *
     }
     // the decode kernel first: its CTAs take their places, the CRC kernel's CTAs get what is left and then every
     // slot a finished decode CTA frees
+    static const bool crc_first = [] { const char *e = getenv("X3_CRC_FIRST"); return e && e[0] == '1'; }();
+    if (crc_first) {
+      t_crc.start();
+      ee = launch_crc(da, hint, s2);
+      t_crc.stop();
+      if (ee != cudaSuccess) return ee;
+    }
     t_dec.start();
     ee = launch_decode(da, hint, st);
     t_dec.stop();
     if (ee != cudaSuccess) return ee;
-    t_crc.start();
-    ee = launch_crc(da, hint, s2);
-    t_crc.stop();
+    if (!crc_first) {
+      t_crc.start();
+      ee = launch_crc(da, hint, s2);
+      t_crc.stop();
+    }
     g_launches += 2;
     if (ee != cudaSuccess) return ee;
     if (s2 != st) {

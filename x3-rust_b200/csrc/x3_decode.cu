@@ -16,6 +16,8 @@
 //      shared-memory ring filled by cp.async one block ahead, and writes whole 32-byte sectors (one 256-bit store).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "x3_dec_core.cuh"
 #include "x3_kernels.h"
 #include "x3_lookback.cuh"
@@ -471,7 +473,7 @@ struct CrcRingSource {
     issue_one();   // block b + 7 goes to the slot of block b - 1, whose words were consumed before this call
   }
 };
-__global__ void __launch_bounds__(X3_CRC_THREADS) crc_frames_kernel(const DecodeArgs a_in) {
+__global__ void __launch_bounds__(X3_CRC_THREADS, 1024 / X3_CRC_THREADS) crc_frames_kernel(const DecodeArgs a_in) {   // <= 64 registers
   DecodeArgs a = a_in;
   if (a.len_dev) a.stream_len = *a.len_dev < a.stream_len ? *a.len_dev : a.stream_len;
   __shared__ uint16_t s_T[256];  // byte table, for payloads at odd addresses only
@@ -816,7 +818,11 @@ cudaError_t launch_crc(const DecodeArgs &a, unsigned long long n_frames_hint, cu
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (n_frames_hint < 1) n_frames_hint = 1;
   unsigned long long g = (n_frames_hint * (X3_CRC_FOLD ? 1ull : 32ull) + X3_CRC_THREADS - 1ull) / X3_CRC_THREADS;  // one thread / one warp per frame
-  const unsigned long long cap = (unsigned long long)sms * (2048ull / X3_CRC_THREADS);
+  unsigned long long cap = (unsigned long long)sms * (2048ull / X3_CRC_THREADS);
+  {
+    static const long per_sm = [] { const char *e = getenv("X3_CRC_CTAS_PER_SM"); return e ? atol(e) : 0L; }();   // tuning runs
+    if (per_sm > 0) cap = (unsigned long long)sms * (unsigned long long)per_sm;
+  }
   if (g > cap) g = cap;
   crc_frames_kernel<<<(unsigned)g, X3_CRC_THREADS, 0, stream>>>(a);
   return cudaGetLastError();

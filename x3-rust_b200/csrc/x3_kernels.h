@@ -17,7 +17,7 @@ enum : int { kEncKernelGeneric = 0, kEncKernelFast = 1, kEncKernelStrip = 2 };
 #define X3_DEC_THREADS 128
 #endif
 #ifndef X3_DEC_MINBLOCKS
-#define X3_DEC_MINBLOCKS 5
+#define X3_DEC_MINBLOCKS 7
 #endif
 constexpr int kDecThreads = X3_DEC_THREADS;
 constexpr int kScanThreads = 256;

@@ -319,6 +319,28 @@ def test_cpp_cli_round_trip(pkg, oracle, tmp_path):
     r = subprocess.run([exe, "-i", str(tmp_path / "bad.x3a"), "-o", str(tmp_path / "bad.wav")], capture_output=True, text=True)
     assert r.returncode == 1 and "FrameHeaderInvalidPayloadCRC" in r.stderr
     assert os.path.getsize(tmp_path / "bad.wav") == 44
+    # the C++ X3aReader streams the file in pieces cut at frame boundaries: a larger file in 64 KiB pieces (each holds
+    # a dozen frames) gives the same WAV as in one piece; a bad frame in a later piece keeps everything before it
+    big = oracle.synth(2, 0x58330002, 384000, 0, 1234567)
+    ref_big, _ = oracle.x3a_encode(big, 384000)
+    (tmp_path / "big.x3a").write_bytes(ref_big.tobytes())
+    env = dict(os.environ, X3_STREAM_CHUNK="65536")
+    r = subprocess.run([exe, "-i", str(tmp_path / "big.x3a"), "-o", str(tmp_path / "big.wav")], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    data = (tmp_path / "big.wav").read_bytes()
+    assert len(data) == 44 + 2 * big.size and np.array_equal(np.frombuffer(data[44:], dtype=np.int16), big)
+    assert int.from_bytes(data[40:44], "little") == 2 * big.size and int.from_bytes(data[4:8], "little") == 36 + 2 * big.size
+    bad = bytearray(ref_big.tobytes())
+    frames = np.frombuffer(bytes(bad[320:]), dtype=np.uint8)
+    pos = 0
+    for _ in range(100):                                   # the start of frame 100, well past the first pieces
+        pos += 20 + ((int(frames[pos + 6]) << 8) | int(frames[pos + 7]))
+    bad[320 + pos + 20 + 77] ^= 0x10
+    (tmp_path / "bad2.x3a").write_bytes(bytes(bad))
+    r = subprocess.run([exe, "-i", str(tmp_path / "bad2.x3a"), "-o", str(tmp_path / "bad2.wav")], capture_output=True, text=True, env=env)
+    assert r.returncode == 1 and "FrameHeaderInvalidPayloadCRC" in r.stderr
+    data = (tmp_path / "bad2.wav").read_bytes()
+    assert len(data) == 44 + 2 * 100 * 10000 and np.array_equal(np.frombuffer(data[44:], dtype=np.int16), big[:1000000])
 
 
 def test_encode_host_pipelined_chunks(pkg, dev, oracle):

@@ -16,6 +16,7 @@
 #include <array>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -255,9 +256,7 @@ inline std::vector<int16_t> read_mono16(const std::string &path, uint32_t *fs) {
   if (!have_fmt) throw std::runtime_error("WAV has no fmt chunk");
   return pcm;
 }
-inline void write_mono16(const std::string &path, uint32_t fs, const int16_t *pcm, size_t n) {
-  std::ofstream f(path, std::ios::binary);
-  if (!f) throw X3Error(X3_ERR_IO);
+inline void write_header(std::ostream &f, uint32_t fs, size_t n) {   // canonical 44-byte PCM header for n mono 16-bit samples
   uint8_t h[44] = {'R', 'I', 'F', 'F', 0, 0, 0, 0, 'W', 'A', 'V', 'E', 'f', 'm', 't', ' ', 16, 0, 0, 0, 1, 0, 1, 0};
   auto w32 = [&](int o, uint32_t v) { h[o] = v; h[o + 1] = v >> 8; h[o + 2] = v >> 16; h[o + 3] = v >> 24; };
   w32(4, (uint32_t)(36 + 2 * n));
@@ -267,6 +266,11 @@ inline void write_mono16(const std::string &path, uint32_t fs, const int16_t *pc
   std::memcpy(h + 36, "data", 4);
   w32(40, (uint32_t)(2 * n));
   f.write(reinterpret_cast<const char *>(h), 44);
+}
+inline void write_mono16(const std::string &path, uint32_t fs, const int16_t *pcm, size_t n) {
+  std::ofstream f(path, std::ios::binary);
+  if (!f) throw X3Error(X3_ERR_IO);
+  write_header(f, fs, n);
   f.write(reinterpret_cast<const char *>(pcm), (std::streamsize)(2 * n));
 }
 }  // namespace wav
@@ -347,65 +351,140 @@ inline void parse_xml(const std::string &xml, uint32_t *fs, Parameters *params, 
   *params = Parameters(std::stoul(sbl), Parameters::DEFAULT_BLOCKS_PER_FRAME, {{ids[0], ids[1], ids[2]}}, {{ths[0], ths[1], ths[2]}});
 }
 
-class X3aReader {  // decodefile.rs:47-137; the file is decoded on the GPU in one call, frames are then handed out
+// decodefile.rs:47-137.  The file is read in pieces of `chunk_bytes` (32 MiB unless X3_STREAM_CHUNK says otherwise), each
+// piece is cut at the last whole frame by the reference's own walk (header, payload_len, next header), decoded on the
+// GPU in one call, and the frames are handed out one at a time; only the current piece is in memory.  The piece that
+// reaches the end of the file is decoded as it is (a truncated last frame, a junk tail, a bad header: decode_stream
+// reports what the reference would).
+class X3aReader {
  public:
-  static X3aReader open(const std::string &filename, bool quiet = false) { return X3aReader(filename, quiet); }
+  static X3aReader open(const std::string &filename, bool quiet = false, size_t chunk_bytes = 0) {
+    return X3aReader(filename, quiet, chunk_bytes);
+  }
   const X3aSpec &spec() const { return spec_; }
   size_t frame_errors() const { return frame_errors_; }
   // returns false at the end of the stream (Ok(None)); throws what the reference would return as Err
   bool decode_next_frame(std::vector<int16_t> &wav_buf, size_t *samples) {
-    if (next_ < sizes_.size()) {
-      wav_buf.assign(pcm_.begin() + (std::ptrdiff_t)starts_[next_], pcm_.begin() + (std::ptrdiff_t)(starts_[next_] + sizes_[next_]));
-      *samples = sizes_[next_++];
-      return true;
+    while (next_ >= sizes_.size()) {
+      if (final_rc_ != X3_OK) { int rc = final_rc_; final_rc_ = X3_OK; done_ = true; throw X3Error(rc); }
+      if (done_ || !next_batch()) return false;
     }
-    if (final_rc_ != X3_OK) { int rc = final_rc_; final_rc_ = X3_OK; throw X3Error(rc); }
-    return false;
+    wav_buf.assign(pcm_.begin() + (std::ptrdiff_t)starts_[next_], pcm_.begin() + (std::ptrdiff_t)(starts_[next_] + sizes_[next_]));
+    *samples = sizes_[next_++];
+    return true;
   }
-  const std::vector<int16_t> &all_samples() const { return pcm_; }
+  // the frames of the current batch that have not been handed out yet, as one run of samples (x3a_to_wav)
+  bool decode_batch(const int16_t **pcm, size_t *samples) {
+    while (next_ >= sizes_.size()) {
+      if (final_rc_ != X3_OK) { int rc = final_rc_; final_rc_ = X3_OK; done_ = true; throw X3Error(rc); }
+      if (done_ || !next_batch()) return false;
+    }
+    *pcm = pcm_.data() + starts_[next_];
+    *samples = pcm_.size() - starts_[next_];
+    next_ = sizes_.size();
+    return true;
+  }
 
  private:
-  X3aReader(const std::string &filename, bool quiet) {
-    std::ifstream f(filename, std::ios::binary);
-    if (!f) throw std::runtime_error("cannot open " + filename);  // File::open(..).unwrap(), decodefile.rs:60
-    std::vector<uint8_t> d((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
-    if (d.size() < 8) throw X3Error(X3_ERR_IO);
-    if (std::memcmp(d.data(), Archive::ID, 8)) throw X3Error(X3_ERR_ARCHIVE_INVALID_KEY);  // decodefile.rs:147-149
-    if (d.size() < 28) throw X3Error(X3_ERR_IO);
-    FrameHeader h = decoder::read_frame_header(d.data() + 8, 20);
-    if (d.size() < 28 + h.payload_len) throw X3Error(X3_ERR_IO);
-    parse_xml(std::string(d.begin() + 28, d.begin() + 28 + (std::ptrdiff_t)h.payload_len), &spec_.sample_rate, &spec_.params, quiet);
+  X3aReader(const std::string &filename, bool quiet, size_t chunk_bytes) : f_(filename, std::ios::binary) {
+    if (!f_) throw std::runtime_error("cannot open " + filename);  // File::open(..).unwrap(), decodefile.rs:60
+    const char *env = std::getenv("X3_STREAM_CHUNK");
+    chunk_ = chunk_bytes ? chunk_bytes : (env && *env ? (size_t)std::strtoull(env, nullptr, 10) : (size_t)32 << 20);
+    if (chunk_ < 64 * 1024) chunk_ = 64 * 1024;   // a piece must hold at least one frame (< 32 KiB)
+    uint8_t head[28];
+    if (!f_.read(reinterpret_cast<char *>(head), 8)) throw X3Error(X3_ERR_IO);
+    if (std::memcmp(head, Archive::ID, 8)) throw X3Error(X3_ERR_ARCHIVE_INVALID_KEY);  // decodefile.rs:147-149
+    if (!f_.read(reinterpret_cast<char *>(head) + 8, 20)) throw X3Error(X3_ERR_IO);
+    FrameHeader h = decoder::read_frame_header(head + 8, 20);
+    std::string xml(h.payload_len, '\0');
+    if (h.payload_len && !f_.read(&xml[0], (std::streamsize)h.payload_len)) throw X3Error(X3_ERR_IO);
+    parse_xml(xml, &spec_.sample_rate, &spec_.params, quiet);
     spec_.channels = h.channels;
-    const uint8_t *frames = d.data() + 28 + h.payload_len;
-    const size_t flen = d.size() - 28 - h.payload_len;
-    x3_decode_result r;
-    pcm_ = decoder::decode_stream(frames, flen, spec_.params, &final_rc_, &r);
-    frame_errors_ = (size_t)r.frame_errors;
-    size_t pos = 0, start = 0;
-    for (uint64_t i = 0; i < r.frames; i++) {
-      FrameHeader fh = decoder::read_frame_header(frames + pos, 20);
-      sizes_.push_back(fh.samples);
-      starts_.push_back(start);
-      start += fh.samples;
-      pos += 20 + fh.payload_len;
+  }
+  // whole frames at the front of buf: their bytes; `stopped` when a header is bad or a frame is longer than the
+  // reference's read buffer -- the decode of the rest of the file reports that
+  static size_t walk(const std::vector<uint8_t> &buf, bool *stopped) {
+    size_t pos = 0;
+    *stopped = false;
+    while (buf.size() - pos > 20) {
+      x3_frame_header h;
+      if (x3_read_frame_header(buf.data() + pos, 20, &h) != X3_OK) { *stopped = true; return pos; }
+      if (buf.size() - pos - 20 < h.payload_len) break;   // continues in the part of the file not read yet
+      pos += 20 + h.payload_len;
+      if (h.payload_len > 24 * 1024) { *stopped = true; return pos; }   // X3_READ_BUFFER_SIZE, decodefile.rs:44,118-121
+    }
+    return pos;
+  }
+  bool next_batch() {
+    for (;;) {
+      if (!eof_) {
+        const size_t old = carry_.size();
+        carry_.resize(old + chunk_);
+        f_.read(reinterpret_cast<char *>(carry_.data() + old), (std::streamsize)chunk_);
+        const size_t got = (size_t)f_.gcount();
+        carry_.resize(old + got);
+        if (got < chunk_) eof_ = true;
+      }
+      bool stopped = false;
+      size_t take = carry_.size();
+      if (!eof_) {
+        take = walk(carry_, &stopped);
+        if (stopped) {   // hand over everything that is left: the decode reports the bad frame
+          std::vector<uint8_t> rest((std::istreambuf_iterator<char>(f_)), std::istreambuf_iterator<char>());
+          carry_.insert(carry_.end(), rest.begin(), rest.end());
+          eof_ = true;
+          take = carry_.size();
+        } else if (take == 0) {
+          continue;      // not one whole frame yet
+        }
+      }
+      if (eof_) done_ = true;
+      x3_decode_result r;
+      pcm_ = decoder::decode_stream(carry_.data(), take, spec_.params, &final_rc_, &r);
+      frame_errors_ += (size_t)r.frame_errors;
+      sizes_.clear();
+      starts_.clear();
+      next_ = 0;
+      size_t pos = 0, start = 0;
+      for (uint64_t i = 0; i < r.frames; i++) {
+        FrameHeader fh = decoder::read_frame_header(carry_.data() + pos, 20);
+        sizes_.push_back(fh.samples);
+        starts_.push_back(start);
+        start += fh.samples;
+        pos += 20 + fh.payload_len;
+      }
+      if (final_rc_ != X3_OK || r.frame_errors) done_ = true;   // the reference stops at the first bad frame
+      carry_.erase(carry_.begin(), carry_.begin() + (std::ptrdiff_t)take);
+      return !sizes_.empty() || final_rc_ != X3_OK;
     }
   }
+  std::ifstream f_;
   X3aSpec spec_;
-  std::vector<int16_t> pcm_;
+  std::vector<uint8_t> carry_;           // bytes read but not decoded yet (a partial frame)
+  std::vector<int16_t> pcm_;             // PCM of the current batch
   std::vector<size_t> sizes_, starts_;
-  size_t next_ = 0, frame_errors_ = 0;
+  size_t next_ = 0, frame_errors_ = 0, chunk_ = 0;
+  bool eof_ = false, done_ = false;
   int final_rc_ = X3_OK;
 };
 
 inline void x3a_to_wav(const std::string &x3a_filename, const std::string &wav_filename, bool quiet = false) {  // decodefile.rs:189-212
   X3aReader rd = X3aReader::open(x3a_filename, quiet);
-  std::vector<int16_t> buf, all;
-  size_t n = 0;
+  // the WAV is written batch by batch; its two length fields are patched at the end (hound does the same on finalize)
+  std::ofstream f(wav_filename, std::ios::binary);
+  if (!f) throw X3Error(X3_ERR_IO);
+  wav::write_header(f, rd.spec().sample_rate, 0);
+  size_t total = 0, n = 0;
+  const int16_t *pcm = nullptr;
   int pending = X3_OK;
   try {
-    while (rd.decode_next_frame(buf, &n)) all.insert(all.end(), buf.begin(), buf.end());
+    while (rd.decode_batch(&pcm, &n)) {
+      f.write(reinterpret_cast<const char *>(pcm), (std::streamsize)(2 * n));
+      total += n;
+    }
   } catch (const X3Error &e) { pending = e.code(); }
-  wav::write_mono16(wav_filename, rd.spec().sample_rate, all.data(), all.size());  // samples before the error are kept
+  f.seekp(0);
+  wav::write_header(f, rd.spec().sample_rate, total);   // samples before the error are kept
   if (pending != X3_OK) throw X3Error(pending);
 }
 }  // namespace decodefile

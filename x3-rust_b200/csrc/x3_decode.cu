@@ -40,6 +40,17 @@ struct Cand {
   uint32_t payload_crc;
 };
 
+// Stream-ordered API: the stream's length lies on the device (ScanArgs::len_dev); the length the host passed is only an
+// upper bound, and so is the number of tiles derived from it.
+__device__ __forceinline__ void apply_device_len(ScanArgs &a) {
+  if (a.len_dev) {
+    const unsigned long long v = *a.len_dev;
+    a.stream_len = v < a.stream_len ? v : a.stream_len;
+    const unsigned long long t = (a.stream_len + a.tile_bytes - 1ull) / a.tile_bytes;
+    a.n_tiles = t < a.n_tiles ? (uint32_t)t : a.n_tiles;
+  }
+}
+
 // decoder::read_frame_header checks (decoder.rs:69-118) on 20 bytes at p (p is 2-byte aligned)
 __device__ bool header_valid(const uint8_t *p, const uint16_t *T, Cand &c) {
   const uint16_t *h = reinterpret_cast<const uint16_t *>(p);
@@ -89,7 +100,7 @@ __device__ __noinline__ void examine_piece(const ScanArgs &a, const uint16_t *s_
 
 __global__ void __launch_bounds__(kScanThreads) scan_headers_kernel(const ScanArgs a_in) {
   ScanArgs a = a_in;
-  if (a.len_dev) a.stream_len = *a.len_dev < a.stream_len ? *a.len_dev : a.stream_len;   // stream-ordered API: the length lies on the device
+  apply_device_len(a);
   __shared__ uint16_t s_T[512];  // T_0, T_1 of the CRC bank are enough for halfword updates
   __shared__ Cand s_cand[kScanCap];
   __shared__ uint32_t s_rank[kScanCap];
@@ -217,7 +228,7 @@ __device__ __noinline__ unsigned long long first_header_in_piece(const ScanArgs 
 #endif
 __global__ void __launch_bounds__(kHopThreads, X3_HOP_MINBLOCKS) hop_index_kernel(const ScanArgs a_in) {
   ScanArgs a = a_in;
-  if (a.len_dev) a.stream_len = *a.len_dev < a.stream_len ? *a.len_dev : a.stream_len;   // stream-ordered API: the length lies on the device
+  apply_device_len(a);
   __shared__ uint16_t s_T[512];
   __shared__ unsigned long long s_pos[kHopWarps][kHopCap];
   const int tid = threadIdx.x;
@@ -320,7 +331,9 @@ __global__ void __launch_bounds__(kHopThreads, X3_HOP_MINBLOCKS) hop_index_kerne
 }
 
 // Exclusive prefix over the tiles of (frames << 38 | samples), in place; totals to result[0], result[1].  One CTA.
-__global__ void __launch_bounds__(1024) tile_prefix_kernel(const ScanArgs a) {
+__global__ void __launch_bounds__(1024) tile_prefix_kernel(const ScanArgs a_in) {
+  ScanArgs a = a_in;
+  apply_device_len(a);
   __shared__ unsigned long long s_warp[32];
   const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
   const uint32_t per = (a.n_tiles + 1023u) / 1024u;
@@ -358,7 +371,9 @@ __global__ void __launch_bounds__(1024) tile_prefix_kernel(const ScanArgs a) {
 }
 
 // One warp per tile: the tile's records go to their final place in the frame table.
-__global__ void __launch_bounds__(256) place_frames_kernel(const ScanArgs a) {
+__global__ void __launch_bounds__(256) place_frames_kernel(const ScanArgs a_in) {
+  ScanArgs a = a_in;
+  apply_device_len(a);
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < a.n_tiles; t += warps) {
@@ -381,7 +396,7 @@ __global__ void __launch_bounds__(256) place_frames_kernel(const ScanArgs a) {
 // (decodefile.rs:114-116) follows.
 __global__ void check_chain_kernel(const ScanArgs a_in) {
   ScanArgs a = a_in;
-  if (a.len_dev) a.stream_len = *a.len_dev < a.stream_len ? *a.len_dev : a.stream_len;   // stream-ordered API: the length lies on the device
+  apply_device_len(a);
   const unsigned long long n = a.result[0];
   const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;

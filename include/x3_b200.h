@@ -13,7 +13,8 @@
  *
  * Threading: entry points are re-entrant; concurrent calls may share a device. `*_device` calls are
  * stream-ordered on `cuda_stream` (a cudaStream_t, NULL = default stream) and synchronise that stream
- * once before returning, because they report lengths / error codes to the host.
+ * once before returning, because they report lengths / error codes to the host; the `*_device_async`
+ * variants only enqueue work and leave their results on the device.
  */
 #ifndef X3_B200_H
 #define X3_B200_H

@@ -671,3 +671,14 @@ def test_stream_ordered_api_matches_sync(pkg, dev, oracle):
     dev.encode_tensor_async(pcm, tiny, enc_res, p)
     torch.cuda.synchronize()
     assert enc_res[1].item() & 1
+
+
+@pytest.mark.parametrize("tool,cases", [("fuzz_gpu.py", 200), ("fuzz_params_gpu.py", 300)])
+def test_randomised_parity(tool, cases):
+    """tools/fuzz_gpu.py (random signals, lengths and damage, Parameters::default()) and tools/fuzz_params_gpu.py (random
+    Parameters) against the oracle: a short run of each; the tools take a case count and a seed for longer ones."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", tool), str(cases), "4242"], capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0 and "0 failures" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
